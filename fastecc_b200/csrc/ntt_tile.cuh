@@ -1,0 +1,269 @@
+// Tile-level decimation-in-time NTT over GF(0xFFF00001): the code every pass kernel runs per 64 KiB tile.
+//
+// This header is the B200 counterpart of the reference's inner loops
+//     IterativeNTT_Steps  ntt.cpp:251-284   (radix-2 butterflies across blocks, inner loop over the SIZE words)
+//     revbin_permute      ntt.cpp:292-309   (here: bit-reversed *addressing* when a tile is loaded, no data pass)
+//     MFA twiddle loop    ntt.cpp:421-431   (here: folded into the butterfly twiddles of the next pass, see below)
+//     scaling loop        RS.cpp:51-59      (here: folded into butterfly twiddles + one uniform pre-scale)
+// It is written as plain `__host__ __device__` code over an abstract "thread id" so that exactly the same
+// index/twiddle logic can be executed thread-by-thread on the CPU (tests/emulate_tile.cpp) before it ever
+// touches a GPU.
+//
+// Geometry.  A tile is R = 2^LR rows (blocks) x WT words, R*WT = 16384 words = 4096 16-byte chunks (64 KiB of
+// shared memory).  256 threads; thread (j, q) owns chunk column q (4 consecutive words of every row: the
+// word dimension is a pure batch dimension, SURVEY 7 "hard part 2") and, in every round, 16 rows.  With
+// Q = WT/4 chunks per row:  q = tid % Q,  j = tid / Q  in [0, R/16).
+//
+// Rounds.  A size-R DIT transform runs ceil(LR/4) rounds; round k handles index bits [lb, lb+4), lb = min(4k, LR-4),
+// executing the radix-2 stages for bits >= 4k only.  In a round a thread holds the 16 slots
+//     r_i = ((j >> lb) << (lb+4)) | (i << lb) | (j & (2^lb - 1)),   i = 0..15
+// in registers (16 x uint4), performs up to 4 stages x 8 butterflies x 4 words, and writes the slots back in
+// place; one block barrier separates rounds.  Slot r of a DIT transform initially holds input element
+// bitrev_LR(r) and finally holds output element r.
+//
+// Twiddles.  All twiddles are powers of g = GF_Root(2^20) (GF(p).cpp:267-276).  A transform is described by two
+// exponents (mod 2^20):  zeta = g^z is the primitive R-th root used by this tile, theta = g^t an *input twist*:
+// the transform computes  X[k] = sum_n x[n] * theta^n * zeta^(n k).  A twisted DIT costs exactly as much as a
+// plain one: the stage that pairs slots differing in bit b uses, for the pair whose low b bits are n,
+//     T[2^b + n] = g^( 2^(LR-1-b) * (z*n + t) )                                   (heap-ordered table, R-1 entries)
+// (derivation in DESIGN.md section 3).  Four-step twiddles (ntt.cpp:421-431) and the RS scaling root_2N^i
+// (RS.cpp:54) are input twists of the following pass, so they cost no multiplications at all.
+#pragma once
+#include "gf.cuh"
+
+#if defined(__CUDACC__)
+#define FECC_HD __host__ __device__ __forceinline__
+#else
+#define FECC_HD inline
+#endif
+
+namespace fecc {
+
+constexpr int kThreads        = 256;
+constexpr int kTileChunks     = 4096;            // 16-byte chunks per tile
+constexpr int kTileBytes      = kTileChunks * 16;
+constexpr int kMaxLogR        = 10;
+constexpr int kMinLogR        = 4;
+
+struct Xform { uint32_t z, t0, t1; };            // tile root g^z; input twist g^(t0 + set*t1)   (exponents mod 2^20)
+
+struct PassParams {
+    const uint32_t* src;
+    uint32_t*       dst;
+    const uint4*    tw;                          // g^e for e in [0, 2^20): {w, Whi, Wlo, 0}
+    uint32_t pitch4;                             // row pitch in 16-byte chunks
+    uint32_t s4;                                 // valid 16-byte chunks per row (ceil(SIZE/4))
+    uint32_t log_r;                              // log2(rows per tile)
+    uint32_t nsets;                              // number of independent row sets
+    uint32_t nstrips;                            // ceil(s4 / Q)
+    uint32_t strips_per_item;                    // consecutive strips of one set handled by one CTA visit
+    unsigned long long src_set_stride, src_row_stride, dst_set_stride, dst_row_stride;   // in rows
+    uint32_t nxf;                                // 1, or 2 = two transforms back to back on the same tile
+    Xform    xf[2];
+    uint32_t prescale;                           // multiply every input word by the constant below (1/N)
+    uint32_t pw, pwhi, pwlo;
+    uint32_t canonical_out;                      // reduce stored words to [0,P)
+    uint32_t parity;                             // Q==4 layout: swap the two rows of a pair when popcount(row>>1) is odd
+};
+
+FECC_HD uint32_t bitrev(uint32_t x, uint32_t bits)
+{
+#if defined(__CUDA_ARCH__)
+    return __brev(x) >> (32 - bits);
+#else
+    uint32_t r = 0; for (uint32_t i = 0; i < bits; i++) r |= ((x >> i) & 1u) << (bits - 1 - i); return r;
+#endif
+}
+FECC_HD uint32_t popc32(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return (uint32_t)__builtin_popcount(x);
+#endif
+}
+
+// chunk index (in uint4 units) of (physical row p, chunk q) inside the tile
+FECC_HD uint32_t tile_chunk(uint32_t p, uint32_t q, uint32_t qlog, uint32_t parity)
+{
+    if (parity) p ^= popc32(p >> 1) & 1u;
+    return (p << qlog) | q;
+}
+
+// number of rounds and per-round (lb, bmin) of a size-2^LR transform
+FECC_HD uint32_t num_rounds(uint32_t LR) { return (LR + 3) >> 2; }
+FECC_HD void round_bits(uint32_t LR, uint32_t k, uint32_t& lb, uint32_t& bmin)
+{
+    bmin = 4 * k;
+    lb = (bmin + 4 <= LR) ? bmin : LR - 4;
+}
+
+// exponent of heap entry idx (1 <= idx < R) of the stage table
+FECC_HD uint32_t table_exponent(uint32_t idx, uint32_t LR, uint32_t z, uint32_t t)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t b = 31 - __clz(idx);
+#else
+    uint32_t b = 31 - (uint32_t)__builtin_clz(idx);
+#endif
+    uint32_t n = idx - (1u << b);
+    return ((z * n + t) << (LR - 1 - b)) & (gf::M - 1);
+}
+
+// One butterfly on 4 words:  (a, b) <- (a + w*b, a - w*b)
+FECC_HD void bfly4(uint4& a, uint4& b, const uint4& w, uint32_t zero)
+{
+    uint32_t v;
+    v = gf::mul(b.x, w.x, w.y, w.z, zero); b.x = gf::subl(a.x, v); a.x = gf::addl(a.x, v);
+    v = gf::mul(b.y, w.x, w.y, w.z, zero); b.y = gf::subl(a.y, v); a.y = gf::addl(a.y, v);
+    v = gf::mul(b.z, w.x, w.y, w.z, zero); b.z = gf::subl(a.z, v); a.z = gf::addl(a.z, v);
+    v = gf::mul(b.w, w.x, w.y, w.z, zero); b.w = gf::subl(a.w, v); a.w = gf::addl(a.w, v);
+}
+
+// Slot bookkeeping of one thread in one round.
+struct RoundCtx {
+    uint32_t lb, bmin;        // bits [lb, lb+4) are in-thread; stages for bits >= bmin are executed
+    uint32_t jbase;           // slot index with the in-thread bits zero
+    uint32_t jlow;            // low lb bits of j (= low lb bits of every slot of this thread)
+};
+
+FECC_HD RoundCtx make_round(uint32_t LR, uint32_t k, uint32_t j)
+{
+    RoundCtx c;
+    round_bits(LR, k, c.lb, c.bmin);
+    c.jlow  = j & ((1u << c.lb) - 1u);
+    c.jbase = ((j >> c.lb) << (c.lb + 4)) | c.jlow;
+    return c;
+}
+
+// The register-resident part of a round: up to four radix-2 DIT stages on the thread's 16 slots x 4 words.
+// tw points at the heap-ordered stage table of the current transform (shared memory on the device).
+FECC_HD void round_compute(uint4 (&x)[16], const RoundCtx& c, uint32_t LR, const uint4* tw, uint32_t zero)
+{
+#pragma unroll
+    for (int beta = 0; beta < 4; ++beta) {
+        const uint32_t b = c.lb + beta;
+        if (b >= c.bmin && b < LR) {
+            const uint4* twb = tw + (1u << b) + c.jlow;
+#pragma unroll
+            for (int m = 0; m < (1 << beta); ++m) {
+                const uint4 w = twb[(uint32_t)m << c.lb];
+#pragma unroll
+                for (int hi = 0; hi < (8 >> beta); ++hi) {
+                    const int i0 = (hi << (beta + 1)) | m;
+                    const int i1 = i0 | (1 << beta);
+                    bfly4(x[i0], x[i1], w, zero);
+                }
+            }
+        }
+    }
+}
+
+// Where the thread's slot i lives in the tile buffer.  `brev` selects the bit-reversed placement used by the
+// second transform of a fused tile (its DIT input index bitrev(r) is the first transform's output slot).
+FECC_HD uint32_t slot_chunk(const RoundCtx& c, int i, uint32_t q, uint32_t LR, uint32_t qlog, uint32_t brev, uint32_t parity)
+{
+    uint32_t r = c.jbase | ((uint32_t)i << c.lb);
+    uint32_t p = brev ? bitrev(r, LR) : r;
+    return tile_chunk(p, q, qlog, parity);
+}
+
+FECC_HD void prescale16(uint4 (&x)[16], uint32_t w, uint32_t whi, uint32_t wlo, uint32_t zero)
+{
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        x[i].x = gf::mul(x[i].x, w, whi, wlo, zero);
+        x[i].y = gf::mul(x[i].y, w, whi, wlo, zero);
+        x[i].z = gf::mul(x[i].z, w, whi, wlo, zero);
+        x[i].w = gf::mul(x[i].w, w, whi, wlo, zero);
+    }
+}
+
+FECC_HD uint4 canon4(uint4 v) { v.x = gf::canon(v.x); v.y = gf::canon(v.y); v.z = gf::canon(v.z); v.w = gf::canon(v.w); return v; }
+
+// Global row (in rows, relative to the buffer start) that feeds physical tile row p of the FIRST transform:
+// slot p holds DIT input element bitrev(p).
+FECC_HD unsigned long long src_row_of(const PassParams& P, uint32_t set, uint32_t p)
+{
+    return (unsigned long long)set * P.src_set_stride + (unsigned long long)bitrev(p, P.log_r) * P.src_row_stride;
+}
+// Global row that receives output element r (slot r of the LAST transform)
+FECC_HD unsigned long long dst_row_of(const PassParams& P, uint32_t set, uint32_t r)
+{
+    return (unsigned long long)set * P.dst_set_stride + (unsigned long long)r * P.dst_row_stride;
+}
+
+} // namespace fecc
+
+// ---------------------------------------------------------------------------------------------------------------
+// Per-thread steps of a tile.  The kernel (ntt_pass.cu) runs them with block barriers in between; the CPU
+// emulation (tests/emulate_tile.cu) runs each step for tid = 0..255 in turn, which is equivalent because within a
+// step a thread only touches its own slots.
+// ---------------------------------------------------------------------------------------------------------------
+namespace fecc {
+
+struct ThreadPos { uint32_t q, j, qlog, Q; };
+FECC_HD ThreadPos thread_pos(const PassParams& P, uint32_t tid)
+{
+    ThreadPos t; t.qlog = 12 - P.log_r; t.Q = 1u << t.qlog; t.q = tid & (t.Q - 1); t.j = tid >> t.qlog; return t;
+}
+
+// Fill the heap-ordered stage table of transform xfi for row set `set` from the global power table.
+FECC_HD void build_table(const PassParams& P, uint32_t xfi, uint32_t set, uint32_t tid, uint4* tw_s)
+{
+    const uint32_t R = 1u << P.log_r;
+    const uint32_t z = P.xf[xfi].z;
+    const uint32_t t = (P.xf[xfi].t0 + set * P.xf[xfi].t1) & (gf::M - 1);
+    for (uint32_t idx = tid; idx < R; idx += kThreads)
+        if (idx) tw_s[idx] = P.tw[table_exponent(idx, P.log_r, z, t)];
+}
+
+// One round of transform xfi on the thread's 16 slots.  The last round of the last transform stores to global
+// memory (output element r -> row dst_row_of(r)); every other round writes back to the tile in place.
+FECC_HD void run_round(const PassParams& P, uint32_t xfi, uint32_t k, uint32_t tid, uint32_t set, uint32_t strip,
+                       uint4* tile, const uint4* tw_s, uint32_t zero)
+{
+    const uint32_t LR = P.log_r;
+    const ThreadPos tp = thread_pos(P, tid);
+    const uint32_t gcol = strip * tp.Q + tp.q;                 // chunk column inside the row
+    if (gcol >= P.s4) return;                                  // partial last strip: nothing to do for this thread
+    const RoundCtx c = make_round(LR, k, tp.j);
+    const bool first = (xfi == 0 && k == 0);
+    const bool last  = (xfi + 1 == P.nxf) && (k + 1 == num_rounds(LR));
+
+    uint4    x[16];
+    uint32_t off[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { off[i] = slot_chunk(c, i, tp.q, LR, tp.qlog, xfi, P.parity); x[i] = tile[off[i]]; }
+
+    if (first && P.prescale) prescale16(x, P.pw, P.pwhi, P.pwlo, zero);
+    round_compute(x, c, LR, tw_s, zero);
+
+    if (!last) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) tile[off[i]] = x[i];
+    } else {
+        uint4* dst4 = reinterpret_cast<uint4*>(P.dst);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t r = c.jbase | ((uint32_t)i << c.lb);
+            const unsigned long long row = dst_row_of(P, set, r);
+            dst4[row * P.pitch4 + gcol] = P.canonical_out ? canon4(x[i]) : x[i];
+        }
+    }
+}
+
+// Which global chunk goes to which tile chunk: thread tid moves chunks c = tid + 256*m, m = 0..15.
+FECC_HD bool load_map(const PassParams& P, uint32_t set, uint32_t strip, uint32_t tid, int m,
+                      unsigned long long& src_chunk, uint32_t& tile_idx)
+{
+    const uint32_t qlog = 12 - P.log_r, Q = 1u << qlog;
+    const uint32_t c = tid + (uint32_t)kThreads * m;
+    const uint32_t p = c >> qlog, qq = c & (Q - 1);
+    const uint32_t gcol = strip * Q + qq;
+    tile_idx  = tile_chunk(p, qq, qlog, P.parity);
+    src_chunk = src_row_of(P, set, p) * P.pitch4 + gcol;
+    return gcol < P.s4;
+}
+
+} // namespace fecc

@@ -1,0 +1,139 @@
+// Host-side planner: turns "NTT of N blocks" / "RS-encode N blocks" into a list of pass descriptors for
+// ntt_pass_kernel.  Pure host code without CUDA runtime calls, so the same plans drive the GPU (api.cu) and the
+// CPU emulation of the kernels (tests/emulate_tile.cu).
+//
+// What is being planned (reference call stacks):
+//   MFA_NTT<uint32_t,0xFFF00001>(data, N, SIZE, InvNTT)            ntt.cpp:382-447
+//   the timed body of EncodeReedSolomon<uint32_t,0xFFF00001>        RS.cpp:41-63
+// The reference picks an R x C (or R x C x L) split that fits a CPU L2 slice and moves block *pointers*; the
+// result is the unique canonical DFT, so the split is ours to choose.  Here N = N1*N2 with both factors <= 1024
+// (one 64 KiB shared-memory tile holds a whole length-N1 or length-N2 column strip):
+//
+//   NTT  (N > 1024, out of place through a scratch buffer Y so that natural order comes out without a transpose pass):
+//     A'  X -> Y : for each n2, DIT over n1 (rows n1*N2+n2), plain; element k1 goes to row n2*N1+k1
+//     B'  Y -> X : for each k1, DIT over n2 (rows n2*N1+k1) with input twist (w^k1)^n2; k2 goes to row k1+N1*k2
+//   ENCODE (N > 1024, in place, 3 passes instead of 2+2; m = k1 + N1*k2 is the coefficient index):
+//     A   for each n2, inverse DIT over n1 (rows n1*N2+n2), inputs pre-scaled by 1/N
+//     BC  for each k1 (rows k1*N2+.., contiguous): inverse DIT over n2 with input twist (w^-k1)^n2, then
+//         forward DIT over k2 with input twist (rho^N1)^k2          (rho = root_2N, RS.cpp:51)
+//     D   for each j2, forward DIT over k1 (rows k1*N2+j2) with input twist (w^j2 * rho)^k1 -> parity row j1*N2+j2
+//   so the four-step twiddles (ntt.cpp:421-431) and the scaling rho^m (RS.cpp:54-58) never cost a multiplication.
+//   N <= 1024: a single pass (NTT) or a single fused pass (encode).   N < 16: see small_dft.cu.
+#pragma once
+#include <vector>
+#include <stdint.h>
+#include <stddef.h>
+#include "ntt_tile.cuh"
+
+namespace fecc {
+
+inline uint32_t ilog2(size_t n) { uint32_t l = 0; while (((size_t)1 << l) < n) ++l; return l; }
+inline bool     is_pow2(size_t n) { return n && !(n & (n - 1)); }
+
+struct Buffers { uint32_t* x; uint32_t* y; const uint4* tw; uint32_t pitch_words; uint32_t size_words; };
+
+inline PassParams base_pass(const Buffers& b, uint32_t log_r)
+{
+    PassParams p{};
+    p.tw = b.tw;
+    p.pitch4 = b.pitch_words / 4;
+    p.s4 = (b.size_words + 3) / 4;
+    p.log_r = log_r;
+    const uint32_t Q = 4096u >> log_r;
+    p.nstrips = (p.s4 + Q - 1) / Q;
+    p.strips_per_item = p.nstrips >= 16 ? 4 : 1;
+    p.nxf = 1;
+    p.parity = (log_r == 10) ? 1u : 0u;
+    return p;
+}
+
+constexpr uint32_t kM = gf::M;
+inline uint32_t emod(long long e) { return (uint32_t)(((e % (long long)kM) + kM) % kM); }
+
+// Standalone transform.  Result lands in b.x; b.y is scratch (needed only when N > 1024).
+inline std::vector<PassParams> plan_ntt(const Buffers& b, size_t N, bool inverse)
+{
+    std::vector<PassParams> v;
+    const uint32_t LN = ilog2(N);
+    const long long p = (long long)(kM / N) * (inverse ? -1 : 1);       // w = g^p
+    if (LN <= kMaxLogR) {
+        PassParams a = base_pass(b, LN);
+        a.src = b.x; a.dst = b.x; a.nsets = 1;
+        a.src_set_stride = a.dst_set_stride = 0; a.src_row_stride = a.dst_row_stride = 1;
+        a.xf[0] = Xform{emod(p), 0, 0};
+        a.canonical_out = 1;
+        v.push_back(a);
+        return v;
+    }
+    const uint32_t L1 = (LN + 1) / 2, L2 = LN - L1;
+    const unsigned long long N1 = 1ull << L1, N2 = 1ull << L2;
+    PassParams a = base_pass(b, L1);
+    a.src = b.x; a.dst = b.y; a.nsets = (uint32_t)N2;
+    a.src_set_stride = 1;  a.src_row_stride = N2;
+    a.dst_set_stride = N1; a.dst_row_stride = 1;
+    a.xf[0] = Xform{emod(p * (long long)N2), 0, 0};
+    v.push_back(a);
+    PassParams c = base_pass(b, L2);
+    c.src = b.y; c.dst = b.x; c.nsets = (uint32_t)N1;
+    c.src_set_stride = 1; c.src_row_stride = N1;
+    c.dst_set_stride = 1; c.dst_row_stride = N1;
+    c.xf[0] = Xform{emod(p * (long long)N1), 0, emod(p)};
+    c.canonical_out = 1;
+    v.push_back(c);
+    return v;
+}
+
+// RS.cpp:41-63 on N data blocks -> N parity blocks, in place in b.x.
+inline std::vector<PassParams> plan_encode(const Buffers& b, size_t N)
+{
+    std::vector<PassParams> v;
+    const uint32_t LN = ilog2(N);
+    const long long q = (long long)(kM / (2 * N));                      // rho = root_2N = g^q, w = g^(2q)
+    const gf::Tw invN = gf::make_tw(gf::inv((uint32_t)N));              // GF_Inv(N), RS.cpp:51
+    if (LN <= kMaxLogR) {
+        PassParams a = base_pass(b, LN);
+        a.src = b.x; a.dst = b.x; a.nsets = 1;
+        a.src_set_stride = a.dst_set_stride = 0; a.src_row_stride = a.dst_row_stride = 1;
+        a.nxf = 2;
+        a.parity = 0;                                                   // bit-reversed placement between the two transforms
+        a.xf[0] = Xform{emod(-2 * q), 0, 0};
+        a.xf[1] = Xform{emod(2 * q), emod(q), 0};
+        a.prescale = 1; a.pw = invN.w; a.pwhi = invN.whi; a.pwlo = invN.wlo;
+        a.canonical_out = 1;
+        v.push_back(a);
+        return v;
+    }
+    const uint32_t L1 = (LN + 1) / 2, L2 = LN - L1;
+    const unsigned long long N1 = 1ull << L1, N2 = 1ull << L2;
+    PassParams a = base_pass(b, L1);
+    a.src = b.x; a.dst = b.x; a.nsets = (uint32_t)N2;
+    a.src_set_stride = a.dst_set_stride = 1; a.src_row_stride = a.dst_row_stride = N2;
+    a.xf[0] = Xform{emod(-2 * q * (long long)N2), 0, 0};
+    a.prescale = 1; a.pw = invN.w; a.pwhi = invN.whi; a.pwlo = invN.wlo;
+    v.push_back(a);
+    PassParams bc = base_pass(b, L2);
+    bc.src = b.x; bc.dst = b.x; bc.nsets = (uint32_t)N1;
+    bc.src_set_stride = bc.dst_set_stride = N2; bc.src_row_stride = bc.dst_row_stride = 1;
+    bc.nxf = 2;
+    bc.parity = 0;
+    bc.xf[0] = Xform{emod(-2 * q * (long long)N1), 0, emod(-2 * q)};
+    bc.xf[1] = Xform{emod(2 * q * (long long)N1), emod(q * (long long)N1), 0};
+    v.push_back(bc);
+    PassParams d = base_pass(b, L1);
+    d.src = b.x; d.dst = b.x; d.nsets = (uint32_t)N2;
+    d.src_set_stride = d.dst_set_stride = 1; d.src_row_stride = d.dst_row_stride = N2;
+    d.xf[0] = Xform{emod(2 * q * (long long)N2), emod(q), emod(2 * q)};
+    d.canonical_out = 1;
+    v.push_back(d);
+    return v;
+}
+
+// g^e table, e in [0, 2^20): 16 MiB, L2-resident on the device.
+inline void fill_power_table(gf::Tw* t)
+{
+    const uint32_t g = gf::root(kM);
+    uint32_t w = 1;
+    for (uint32_t e = 0; e < kM; ++e) { t[e] = gf::make_tw(w); w = gf::mulmod(w, g); }
+}
+
+} // namespace fecc

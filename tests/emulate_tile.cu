@@ -1,0 +1,80 @@
+// CPU emulation of ntt_pass_kernel: runs the *same* per-thread step functions (ntt_tile.cuh) and the same plans
+// (plan.h) thread-by-thread on the host and checks the result against the oracle (oracle/gfp_oracle.c).
+// Used by tests/test_emulation.py (-m "not gpu"): catches index / twiddle / plan errors without a GPU.
+// Build: nvcc -O2 -o emulate_tile emulate_tile.cu -I../fastecc_b200/csrc -I../oracle ../oracle/liboracle.so
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "plan.h"
+#include "gfp_oracle.h"
+
+using namespace fecc;
+
+static void emulate_pass(const PassParams& P)
+{
+    std::vector<uint4> tile(kTileChunks), tw0(1u << P.log_r), tw1(1u << P.log_r);
+    const uint32_t groups = (P.nstrips + P.strips_per_item - 1) / P.strips_per_item;
+    const uint32_t nitems = P.nsets * groups;
+    const uint32_t nrounds = num_rounds(P.log_r);
+    const uint4* src4 = reinterpret_cast<const uint4*>(P.src);
+    for (uint32_t item = 0; item < nitems; ++item) {
+        const uint32_t set = item / groups, sg = item - set * groups;
+        const uint32_t strip0 = sg * P.strips_per_item;
+        const uint32_t strip1 = std::min(strip0 + P.strips_per_item, P.nstrips);
+        for (uint32_t strip = strip0; strip < strip1; ++strip) {
+            for (auto& c : tile) c = make_uint4(0xDEADBEEF, 0xDEADBEEF, 0xDEADBEEF, 0xDEADBEEF);
+            for (uint32_t tid = 0; tid < kThreads; ++tid)
+                for (int m = 0; m < 16; ++m) {
+                    unsigned long long sc; uint32_t ti;
+                    if (load_map(P, set, strip, tid, m, sc, ti)) tile[ti] = src4[sc];
+                }
+            if (strip == strip0)
+                for (uint32_t tid = 0; tid < kThreads; ++tid) {
+                    build_table(P, 0, set, tid, tw0.data());
+                    if (P.nxf == 2) build_table(P, 1, set, tid, tw1.data());
+                }
+            for (uint32_t xfi = 0; xfi < P.nxf; ++xfi)
+                for (uint32_t k = 0; k < nrounds; ++k)
+                    for (uint32_t tid = 0; tid < kThreads; ++tid)
+                        run_round(P, xfi, k, tid, set, strip, tile.data(), xfi ? tw1.data() : tw0.data(), 0);
+        }
+    }
+}
+
+static std::vector<gf::Tw> g_tw;
+
+static int check(const char* what, size_t N, size_t S, int mode /*0 fwd,1 inv,2 encode*/)
+{
+    const size_t pitch = (S + 3) / 4 * 4;
+    std::vector<uint32_t> x(N * pitch, 0), y(N * pitch, 0), ref(N * S);
+    oracle_fill_B(ref.data(), N * S);
+    for (size_t i = 0; i < N; i++) memcpy(&x[i * pitch], &ref[i * S], S * 4);
+    Buffers b{x.data(), y.data(), reinterpret_cast<const uint4*>(g_tw.data()), (uint32_t)pitch, (uint32_t)S};
+    std::vector<PassParams> plan = (mode == 2) ? plan_encode(b, N) : plan_ntt(b, N, mode == 1);
+    for (auto& p : plan) emulate_pass(p);
+    if (mode == 2) oracle_rs_encode(ref.data(), N, S); else oracle_ntt(ref.data(), N, S, mode);
+    size_t bad = 0;
+    for (size_t i = 0; i < N; i++) for (size_t k = 0; k < S; k++) if (x[i * pitch + k] != ref[i * S + k]) { if (!bad) printf("   first mismatch row %zu word %zu: got %u want %u\n", i, k, x[i*pitch+k], ref[i*S+k]); bad++; }
+    printf("%-8s N=2^%-2u S=%-5zu passes=%zu : %s (%zu mismatches)\n", what, ilog2(N), S, plan.size(), bad ? "FAIL" : "ok", bad);
+    return bad != 0;
+}
+
+int main(int argc, char** argv)
+{
+    g_tw.resize(kM);
+    fill_power_table(g_tw.data());
+    int fails = 0;
+    const bool big = argc > 1 && !strcmp(argv[1], "big");
+    struct Cfg { unsigned ln; size_t s; };
+    std::vector<Cfg> cfgs = { {4, 16}, {5, 8}, {6, 1024}, {7, 1024}, {8, 20}, {9, 36}, {10, 16}, {10, 24}, {11, 16}, {12, 8}, {13, 4}, {7, 513} };
+    if (big) { cfgs.push_back({16, 16}); cfgs.push_back({19, 16}); cfgs.push_back({20, 4}); cfgs.push_back({15, 32}); }
+    for (auto c : cfgs) {
+        const size_t N = (size_t)1 << c.ln;
+        fails += check("ntt-fwd", N, c.s, 0);
+        fails += check("ntt-inv", N, c.s, 1);
+        if (c.ln <= 19) fails += check("encode", N, c.s, 2);
+    }
+    printf("%s\n", fails ? "EMULATION FAILED" : "EMULATION OK");
+    return fails ? 1 : 0;
+}
