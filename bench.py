@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- RS encode GB/s at (n,k)=(2^20,2^19), 4 KiB blocks (BASELINE.json metric), on N B200s.
+
+Own arm (default): one process per GPU (torchrun for N>1).  A step = one full encode (RS.cpp:41-63) of
+N=2^19 data blocks x 4096 B resident in HBM -> 2^19 parity blocks, through the C ABI
+(fastecc_b200_rs_encode_dev).  Throughput convention is the reference's: bytes = 2*N*SIZE*4 per encode
+(RS.cpp:38).  With N>1 GPUs every rank encodes its own independent stripe of 2^19 blocks (weak scaling, no
+data-path collective).
+
+`--impl reference`: times the UNMODIFIED reference CPU encoder (oracle/_ref, compiled from /root/reference by
+oracle/Makefile: AVX2 + OpenMP build, all host threads) on the same config; rank 0 only.
+
+One JSON line on stdout (rank 0).  See DESIGN.md section 7 for how every field is measured.
+"""
+import argparse
+import ctypes
+import json
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+P = 0xFFF00001
+METRIC = "rs_encode_GBps_n2^20_k2^19_4KiB_blocks"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log-n", type=int, default=19, help="log2 of the number of data blocks (headline: 19)")
+    ap.add_argument("--block-bytes", type=int, default=4096)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        load = sorted(s for s, p in zip(sm, pw) if p >= 0.6 * max(pw)) or sorted(sm)
+        return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------- reference CPU arm
+def load_ref_lib():
+    path = os.path.join(ROOT, "oracle", "_ref", "libfastecc_ref.so")
+    if not os.path.exists(path):
+        return None
+    r = ctypes.CDLL(path)
+    r.ref_rs_encode.restype = None                      # RS.cpp:41-63 on a caller-supplied T** table
+    r.ref_rs_encode.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t]
+    r.ref_num_threads.restype = ctypes.c_int
+    r.ref_build_flavour.restype = ctypes.c_char_p
+    return r
+
+
+def load_oracle_port():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    return oracle_lib.load_oracle()
+
+
+def cpu_encode_runner(log_n, size_words):
+    """Returns (fn, kind, cores, label): fn() runs one full CPU encode of 2^log_n x size_words in place."""
+    import numpy as np
+    N = 1 << log_n
+    buf = (np.arange(N * size_words, dtype=np.uint64) % P).astype(np.uint32)
+    r = load_ref_lib()
+    if r is not None:
+        tab = (ctypes.c_void_p * N)()                   # T** data, RS.cpp:31-33; left permuted between steps like the reference leaves it
+        for i in range(N):
+            tab[i] = buf.ctypes.data + i * size_words * 4
+        return (lambda: r.ref_rs_encode(tab, N, size_words)), "reference", int(r.ref_num_threads()), \
+            "unmodified FastECC templates, %s+OpenMP build (oracle/_ref)" % r.ref_build_flavour().decode()
+    o = load_oracle_port()
+    return (lambda: o.oracle_rs_encode(buf.ctypes.data, N, size_words)), "port", int(o.oracle_num_threads()), "oracle/gfp_oracle.c (plain C port, OpenMP)"
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    os.environ.setdefault("OMP_WAIT_POLICY", "active")
+    size_words = args.block_bytes // 4
+    N = 1 << args.log_n
+    fn, kind, cores, label = cpu_encode_runner(args.log_n, size_words)
+    for _ in range(max(1, min(args.warmup, 3))):
+        fn()
+    times = []
+    budget_t0 = time.perf_counter()
+    for _ in range(args.steps):
+        t0 = time.perf_counter(); fn(); times.append(time.perf_counter() - t0)
+        if time.perf_counter() - budget_t0 > 240:          # keep the whole run within a few minutes
+            break
+    total = sum(times)
+    nbytes = 2.0 * N * size_words * 4
+    value = nbytes * len(times) / total / 1e9
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / len(times), "best_ms": 1e3 * min(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic",
+        "config": {"workload": "rs_encode N=2^%d data blocks -> 2^%d parity, %d-byte blocks, GF(0xFFF00001), host memory" % (args.log_n, args.log_n, args.block_bytes),
+                   "bytes_per_step": nbytes, "convention": "2*N*SIZE*4 bytes per encode (RS.cpp:38)"},
+        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": cores, "kind": kind, "sample": "%d full encodes of the workload; %s" % (len(times), label)},
+        "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+    return 0
+
+
+def quick_cpu_baseline(args):
+    """Bounded CPU sample for the own arm's cpu_baseline block: a few full encodes (about 10-30 s of CPU work at most)."""
+    try:
+        os.environ.setdefault("OMP_WAIT_POLICY", "active")
+        size_words = args.block_bytes // 4
+        fn, kind, cores, label = cpu_encode_runner(args.log_n, size_words)
+        fn()
+        times = []
+        t_start = time.perf_counter()
+        while len(times) < 5 and time.perf_counter() - t_start < 20:
+            t0 = time.perf_counter(); fn(); times.append(time.perf_counter() - t0)
+        nbytes = 2.0 * (1 << args.log_n) * size_words * 4
+        return {"value": nbytes / min(times) / 1e9, "unit": "GB/s", "cores": cores, "kind": kind,
+                "sample": "best of %d full encodes of the same workload (mean %.1f ms); %s" % (len(times), 1e3 * sum(times) / len(times), label)}
+    except Exception as e:       # never let the baseline leg break the GPU measurement
+        return {"value": None, "unit": "GB/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
+
+
+# ---------------------------------------------------------------------------------------------------- B200 arm
+def run_b200_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import fastecc_b200 as fe
+    fe.init(local)                      # raises if the CUDA library or an sm_100 GPU is missing: no fallback
+
+    N, S = 1 << args.log_n, args.block_bytes // 4
+    dev = torch.device("cuda", local)
+    data = torch.empty((N, S), dtype=torch.int32, device=dev)
+    flat = data.view(-1)
+    step_elems = 1 << 26
+    for lo in range(0, flat.numel(), step_elems):                      # fill A: data0[i] = i % P  (RS.cpp:28-29)
+        hi = min(lo + step_elems, flat.numel())
+        flat[lo:hi] = (torch.arange(lo, hi, device=dev, dtype=torch.int64) % P).to(torch.int32)
+    nbytes = 2.0 * N * S * 4
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        fe.rs_encode_dev(data)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = fe.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        fe.rs_encode_dev(data)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    launches = fe.kernel_launches() - launches0
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    barrier()
+
+    # ---- end-to-end through the reference-facing host call (T** table, pinned host memory, H2D + D2H inside)
+    e2e = None
+    if not args.no_e2e:
+        hptr = fe.lib().fastecc_b200_host_alloc(N * S * 4)
+        if not hptr:
+            raise SystemExit("pinned allocation failed")
+        harr = np.ctypeslib.as_array((ctypes.c_uint32 * (N * S)).from_address(hptr)).reshape(N, S)
+        harr[:] = (np.arange(N * S, dtype=np.uint64) % P).astype(np.uint32).reshape(N, S)
+        fe.EncodeReedSolomon_body(harr, N, S)                           # warm-up (allocates the device staging buffer)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            fe.EncodeReedSolomon_body(harr, N, S)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e = {"value": world * nbytes * args.e2e_steps / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": N * S * 4, "d2h_bytes_per_step": N * S * 4,
+               "ms_per_step": 1e3 * e2e_s / args.e2e_steps, "api": "fastecc_b200_rs_encode(T** data, N, SIZE) on pinned host blocks"}
+        del harr
+        fe.lib().fastecc_b200_host_free(hptr)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        passes_per_step = launches / max(args.steps, 1)
+        launch_ms = ms / max(launches, 1)
+        achieved = nbytes / (launch_ms * 1e-3) / 1e9              # every pass reads and writes the whole array once
+        out = {
+            "metric": METRIC, "value": world * nbytes * args.steps / (ms * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": "rs_encode N=2^%d data blocks -> 2^%d parity, %d-byte blocks, GF(0xFFF00001), resident in HBM" % (args.log_n, args.log_n, args.block_bytes),
+                       "bytes_per_step": nbytes, "convention": "2*N*SIZE*4 bytes per encode (RS.cpp:38)", "per_gpu_buffer_bytes": N * S * 4,
+                       "l2": "inputs (2 GiB per GPU) are larger than L2; no flush needed", "parallelism": "independent stripe per GPU" if world > 1 else "single GPU",
+                       "passes_per_encode": passes_per_step},
+            "roofline": {"bound": "hbm", "kernel": "ntt_pass_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "note": "algorithmic bytes per launch = 2*N*SIZE*4 (one read + one write of the array per pass); avg launch = timed region / launches"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if e2e:
+            out["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = quick_cpu_baseline(args)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,197 @@
+// extern "C" boundary of fastecc_b200 (include/fastecc_b200.h): context, planning, launches, host<->device staging.
+#include "../../include/fastecc_b200.h"
+#include "plan.h"
+#include "ntt_pass.h"
+#include "small_dft.h"
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+#include <vector>
+#include <atomic>
+
+using namespace fecc;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr; size_t bytes = 0;
+    cudaError_t reserve(size_t need) {
+        if (need <= bytes) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; bytes = 0; }
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e == cudaSuccess) bytes = need;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+struct Context {
+    int device = -1;
+    int num_sms = 0;
+    uint4* d_tw = nullptr;
+    DevBuf scratch;      // Y buffer of the two-pass NTT
+    DevBuf packed;       // repacked copy for unaligned device layouts
+    DevBuf staging;      // device copy for the host (T**) entry points
+    cudaStream_t stream = nullptr;
+};
+
+Context* g_ctx = nullptr;
+std::mutex g_mu;
+std::atomic<unsigned long long> g_launches{0};
+thread_local char g_err[512] = "no error";
+
+int fail(int code, const char* fmt, ...)
+{
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+    return code;
+}
+#define CUDA_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) \
+    return fail(e_ == cudaErrorMemoryAllocation ? FASTECC_B200_ENOMEM : FASTECC_B200_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); } while (0)
+
+int check_shape(size_t N, size_t size, size_t max_log, const char* who)
+{
+    if (size == 0) return fail(FASTECC_B200_EINVAL, "%s: SIZE must be >= 1 word", who);
+    if (!is_pow2(N) || N > ((size_t)1 << max_log))
+        return fail(FASTECC_B200_EINVAL, "%s: N=%zu must be a power of two in [1, 2^%zu] (P-1 = 2^20*4095)", who, N, max_log);
+    if (size > 0xFFFFFFF0u) return fail(FASTECC_B200_EINVAL, "%s: SIZE too large", who);
+    return 0;
+}
+
+// Run the planned passes on an aligned, padded device buffer.
+int run_aligned(Context* c, uint32_t* x, size_t N, size_t size, size_t pitch, int mode /*0 fwd,1 inv,2 encode*/, cudaStream_t st)
+{
+    const uint32_t pitch4 = (uint32_t)(pitch / 4), s4 = (uint32_t)((size + 3) / 4);
+    if (N < 16) {
+        const uint32_t z = (uint32_t)(gf::M / N) * (mode == 1 ? (uint32_t)-1 : 1u) & (gf::M - 1);
+        const uint32_t q = mode == 2 ? (uint32_t)(gf::M / (2 * N)) : 0;
+        const gf::Tw in = gf::make_tw(gf::inv((uint32_t)N));
+        CUDA_TRY(launch_small_dft(x, pitch4, s4, (uint32_t)N, z, mode == 2, q, make_uint4(in.w, in.whi, in.wlo, 0), c->d_tw, st));
+        g_launches++;
+        return 0;
+    }
+    Buffers b{x, nullptr, c->d_tw, (uint32_t)pitch, (uint32_t)size};
+    if (mode != 2 && N > ((size_t)1 << kMaxLogR)) {
+        CUDA_TRY(c->scratch.reserve(N * pitch * sizeof(uint32_t)));
+        b.y = (uint32_t*)c->scratch.p;
+    }
+    std::vector<PassParams> plan = (mode == 2) ? plan_encode(b, N) : plan_ntt(b, N, mode == 1);
+    for (const PassParams& p : plan) { CUDA_TRY(launch_pass(p, c->num_sms, st)); g_launches++; }
+    return 0;
+}
+
+int run_dev(uint32_t* d, size_t N, size_t size, size_t pitch, int mode, void* stream, const char* who)
+{
+    Context* c = g_ctx;
+    if (!c) return fail(FASTECC_B200_ENOINIT, "%s: call fastecc_b200_init() first", who);
+    if (!d) return fail(FASTECC_B200_EINVAL, "%s: null device pointer", who);
+    if (int rc = check_shape(N, size, mode == 2 ? FASTECC_B200_MAX_LOG_N_ENCODE : FASTECC_B200_MAX_LOG_N, who)) return rc;
+    if (pitch < size) return fail(FASTECC_B200_EINVAL, "%s: pitch_words (%zu) < SIZE_words (%zu)", who, pitch, size);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool aligned = (pitch % 4 == 0) && (((uintptr_t)d) % 16 == 0);
+    if (aligned) return run_aligned(c, d, N, size, pitch, mode, st);
+    // unaligned layout: repack into a padded copy, transform, copy the SIZE data words back
+    const size_t ppitch = (size + 3) / 4 * 4;
+    CUDA_TRY(c->packed.reserve(N * ppitch * sizeof(uint32_t)));
+    uint32_t* pk = (uint32_t*)c->packed.p;
+    CUDA_TRY(launch_pack(d, pitch, pk, ppitch, N, (uint32_t)size, st)); g_launches++;
+    if (int rc = run_aligned(c, pk, N, size, ppitch, mode, st)) return rc;
+    CUDA_TRY(launch_unpack(pk, ppitch, d, pitch, N, (uint32_t)size, st)); g_launches++;
+    return 0;
+}
+
+int run_host(uint32_t** data, size_t N, size_t size, int mode, const char* who)
+{
+    Context* c = g_ctx;
+    if (!c) return fail(FASTECC_B200_ENOINIT, "%s: call fastecc_b200_init() first", who);
+    if (!data) return fail(FASTECC_B200_EINVAL, "%s: null block table", who);
+    if (int rc = check_shape(N, size, mode == 2 ? FASTECC_B200_MAX_LOG_N_ENCODE : FASTECC_B200_MAX_LOG_N, who)) return rc;
+    for (size_t i = 0; i < N; i++) if (!data[i]) return fail(FASTECC_B200_EINVAL, "%s: data[%zu] is null", who, i);
+    const size_t pitch = (size + 3) / 4 * 4;
+    CUDA_TRY(c->staging.reserve(N * pitch * sizeof(uint32_t)));
+    uint32_t* dv = (uint32_t*)c->staging.p;
+    cudaStream_t st = c->stream;
+    bool contiguous = true;
+    for (size_t i = 1; i < N; i++) if (data[i] != data[0] + i * size) { contiguous = false; break; }
+    if (pitch != size) CUDA_TRY(cudaMemsetAsync(dv, 0, N * pitch * sizeof(uint32_t), st));
+    if (contiguous) {
+        CUDA_TRY(cudaMemcpy2DAsync(dv, pitch * 4, data[0], size * 4, size * 4, N, cudaMemcpyHostToDevice, st));
+    } else {
+        for (size_t i = 0; i < N; i++) CUDA_TRY(cudaMemcpyAsync(dv + i * pitch, data[i], size * 4, cudaMemcpyHostToDevice, st));
+    }
+    if (int rc = run_aligned(c, dv, N, size, pitch, mode, st)) return rc;
+    if (contiguous) {
+        CUDA_TRY(cudaMemcpy2DAsync(data[0], size * 4, dv, pitch * 4, size * 4, N, cudaMemcpyDeviceToHost, st));
+    } else {
+        for (size_t i = 0; i < N; i++) CUDA_TRY(cudaMemcpyAsync(data[i], dv + i * pitch, size * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int fastecc_b200_init(int device)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_ctx && g_ctx->device == device) return 0;
+    if (g_ctx) return fail(FASTECC_B200_EINVAL, "fastecc_b200_init: already initialised on device %d (one process per GPU)", g_ctx->device);
+    int count = 0;
+    CUDA_TRY(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(FASTECC_B200_EINVAL, "fastecc_b200_init: device %d out of range (%d visible)", device, count);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(FASTECC_B200_ECUDA, "fastecc_b200_init: device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+    Context* c = new Context;
+    c->device = device; c->num_sms = prop.multiProcessorCount;
+    std::vector<gf::Tw> tw(gf::M);
+    fill_power_table(tw.data());
+    CUDA_TRY(cudaMalloc((void**)&c->d_tw, sizeof(gf::Tw) * gf::M));
+    CUDA_TRY(cudaMemcpy(c->d_tw, tw.data(), sizeof(gf::Tw) * gf::M, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    g_ctx = c;
+    return 0;
+}
+
+void fastecc_b200_shutdown(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_ctx) return;
+    cudaSetDevice(g_ctx->device);
+    cudaDeviceSynchronize();
+    g_ctx->scratch.release(); g_ctx->packed.release(); g_ctx->staging.release();
+    if (g_ctx->d_tw) cudaFree(g_ctx->d_tw);
+    if (g_ctx->stream) cudaStreamDestroy(g_ctx->stream);
+    delete g_ctx; g_ctx = nullptr;
+}
+
+const char* fastecc_b200_last_error(void) { return g_err; }
+int fastecc_b200_device(void)  { return g_ctx ? g_ctx->device : -1; }
+int fastecc_b200_num_sms(void) { return g_ctx ? g_ctx->num_sms : 0; }
+unsigned long long fastecc_b200_kernel_launches(void) { return g_launches.load(); }
+
+int fastecc_b200_ntt_u32_dev(uint32_t* d, size_t N, size_t size, size_t pitch, int inverse, void* stream)
+{ return run_dev(d, N, size, pitch, inverse ? 1 : 0, stream, "fastecc_b200_ntt_u32_dev"); }
+
+int fastecc_b200_rs_encode_dev(uint32_t* d, size_t N, size_t size, size_t pitch, void* stream)
+{ return run_dev(d, N, size, pitch, 2, stream, "fastecc_b200_rs_encode_dev"); }
+
+int fastecc_b200_ntt_u32(uint32_t** data, size_t N, size_t size, int inverse)
+{ return run_host(data, N, size, inverse ? 1 : 0, "fastecc_b200_ntt_u32"); }
+
+int fastecc_b200_rs_encode(uint32_t** data, size_t N, size_t size)
+{ return run_host(data, N, size, 2, "fastecc_b200_rs_encode"); }
+
+void* fastecc_b200_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { fail(FASTECC_B200_ENOMEM, "cudaHostAlloc(%zu) failed", bytes); return nullptr; }
+    return p;
+}
+void fastecc_b200_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+} // extern "C"

@@ -1,0 +1,74 @@
+/* fastecc_b200 -- C ABI of the B200 (sm_100a) NTT Reed-Solomon encoder.
+ *
+ * This is the drop-in boundary for the one hot path of Bulat-Ziganshin/FastECC.  The reference has no FFI layer:
+ * its programs textually include the template sources, so the boundary is created at the narrowest existing call
+ * surface.  Each entry point below names the reference interface it replaces (file:line in the reference tree).
+ * All functions return 0 on success and a negative FASTECC_B200_E* code otherwise; fastecc_b200_last_error()
+ * returns a human-readable message for the calling thread.  There is NO CPU fallback: without a usable CUDA
+ * device every compute entry point fails with FASTECC_B200_ECUDA.
+ *
+ * Data model (same as the reference): N blocks of SIZE 32-bit words, words are elements of
+ * GF(P), P = 0xFFF00001, the transform runs across blocks independently for every word column.  Inputs may be
+ * any 32-bit values (they are taken mod P); outputs are canonical residues in [0, P).
+ */
+#ifndef FASTECC_B200_H
+#define FASTECC_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FASTECC_B200_P        0xFFF00001u
+#define FASTECC_B200_MAX_LOG_N        20      /* P-1 = 2^20 * 4095: largest power-of-two transform (main.cpp:326) */
+#define FASTECC_B200_MAX_LOG_N_ENCODE 19      /* encode needs a root of order 2N (RS.cpp:51, README.md:29)        */
+
+enum {
+    FASTECC_B200_OK       =  0,
+    FASTECC_B200_EINVAL   = -1,   /* N not a power of two / out of range, SIZE == 0, bad pitch, null pointer */
+    FASTECC_B200_ECUDA    = -2,   /* CUDA runtime error (message has the cudaError string)                   */
+    FASTECC_B200_ENOMEM   = -3,   /* device or pinned-host allocation failed                                 */
+    FASTECC_B200_ENOINIT  = -4    /* fastecc_b200_init() has not succeeded in this process                   */
+};
+
+/* Process-wide context on one CUDA device: uploads the 16 MiB power table g^e (g = GF_Root(2^20),
+ * GF(p).cpp:267-276) and caches scratch buffers.  Idempotent for the same device.  One process per GPU. */
+int  fastecc_b200_init(int device);
+void fastecc_b200_shutdown(void);
+const char* fastecc_b200_last_error(void);
+int  fastecc_b200_device(void);                 /* device ordinal of the live context, or -1 */
+int  fastecc_b200_num_sms(void);
+
+/* ---- reference call surface, host memory ---------------------------------------------------------------------
+ * Replaces  template<T,P> void MFA_NTT(T** data, size_t N, size_t SIZE, bool InvNTT)      ntt.cpp:382-383
+ * for <uint32_t,0xFFF00001>; call sites RS.cpp:41,63 and main.cpp:234,272,286.
+ * data[i] -> SIZE words of block i (host memory, pageable or pinned).  In place: on return data[i] addresses
+ * result block i; the pointer table itself is left untouched (the reference permutes it, callers only read
+ * through data[i]).  The inverse transform is unnormalised, as in the reference.  1 <= N <= 2^20, power of two. */
+int fastecc_b200_ntt_u32(uint32_t** data, size_t N, size_t SIZE_words, int inverse);
+
+/* Replaces the timed body of  template<T,P> void EncodeReedSolomon(size_t N, size_t SIZE)   RS.cpp:41-63
+ * (iNTT, multiply block i by root_2N^i / N, NTT): N data blocks in, N parity blocks out, same buffers.
+ * 1 <= N <= 2^19 (N = 2^20 is rejected: the reference silently computes garbage there, GF(p).cpp:274). */
+int fastecc_b200_rs_encode(uint32_t** data, size_t N, size_t SIZE_words);
+
+/* ---- device-resident variants (what bench.py times as `value`; PCIe excluded) ----------------------------------
+ * d_blocks: device pointer to N rows of pitch_words words each (row i = block i), first SIZE_words of a row
+ * are data.  The fast path needs d_blocks 16-byte aligned and pitch_words % 4 == 0 (columns are processed in
+ * groups of 4 words, so up to 3 pad words per row are read and rewritten); other layouts go through an internal
+ * repack.  stream: a cudaStream_t (NULL = default stream).  Asynchronous with respect to the host. */
+int fastecc_b200_ntt_u32_dev  (uint32_t* d_blocks, size_t N, size_t SIZE_words, size_t pitch_words, int inverse, void* stream);
+int fastecc_b200_rs_encode_dev(uint32_t* d_blocks, size_t N, size_t SIZE_words, size_t pitch_words, void* stream);
+
+/* Counters for benchmarking: kernels launched by this library since init (all entry points). */
+unsigned long long fastecc_b200_kernel_launches(void);
+
+/* Pinned host memory helpers for callers that want the fast host path (cudaHostAlloc / cudaFreeHost). */
+void* fastecc_b200_host_alloc(size_t bytes);
+void  fastecc_b200_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

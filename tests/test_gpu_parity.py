@@ -1,0 +1,212 @@
+"""GPU parity tests (-m gpu): every call goes through the C ABI (include/fastecc_b200.h) and is compared bit for bit
+with the CPU oracle, the committed reference vectors, the golden hashes of SURVEY.md 8c and -- at the full
+BASELINE sizes -- golden hashes plus size-independent properties (round trip, linearity)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = json.load(open(os.path.join(HERE, "golden", "survey_8c.json")))
+V = np.load(os.path.join(HERE, "golden", "vectors.npz"))
+P = 0xFFF00001
+
+
+def to_dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).cuda()
+
+
+def to_host(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+def dev_ntt(fecc, a, inverse):
+    t = to_dev(a); fecc.ntt_dev(t, inverse); return to_host(t)
+
+
+def dev_encode(fecc, a):
+    t = to_dev(a); fecc.rs_encode_dev(t); return to_host(t)
+
+
+SHAPES = [(0, 4), (1, 4), (2, 8), (3, 8), (4, 16), (5, 8), (6, 1024), (7, 1024), (8, 20), (9, 36), (10, 16), (10, 100),
+          (11, 16), (11, 1024), (12, 40), (13, 64), (14, 12), (15, 32), (16, 16), (17, 8), (18, 4)]
+
+
+@pytest.mark.parametrize("L,S", SHAPES)
+def test_dev_ntt_and_encode_match_oracle(fecc, oracle, L, S):
+    N = 1 << L
+    a = ol.fill_B(oracle, N, S)
+    assert np.array_equal(dev_ntt(fecc, a, False), ol.o_ntt(oracle, a, False))
+    assert np.array_equal(dev_ntt(fecc, a, True), ol.o_ntt(oracle, a, True))
+    assert np.array_equal(dev_encode(fecc, a), ol.o_encode(oracle, a))
+
+
+@pytest.mark.parametrize("L,S", [(3, 1), (7, 513), (9, 5), (10, 17), (12, 3), (4, 1023)])
+def test_dev_unaligned_sizes_repack_path(fecc, oracle, L, S):
+    """SIZE not a multiple of 4 words (the reference default is 2052 bytes = 513 words, RS.cpp:74)."""
+    N = 1 << L
+    a = ol.fill_B(oracle, N, S)
+    assert np.array_equal(dev_ntt(fecc, a, False), ol.o_ntt(oracle, a, False))
+    assert np.array_equal(dev_encode(fecc, a), ol.o_encode(oracle, a))
+
+
+def test_dev_padded_pitch_leaves_layout_intact(fecc, oracle):
+    import torch
+    N, S, pitch = 256, 24, 40
+    a = ol.fill_B(oracle, N, S)
+    buf = torch.full((N, pitch), 7, dtype=torch.int32, device="cuda")
+    view = buf[:, :S]
+    view.copy_(to_dev(a))
+    fecc.rs_encode_dev(view)
+    assert np.array_equal(to_host(view.contiguous()), ol.o_encode(oracle, a))
+    assert bool((buf[:, S + (-S % 4):] == 7).all())          # only the 4-word-aligned data columns are touched
+
+
+@pytest.mark.parametrize("L,S", [(0, 3), (2, 1), (4, 16), (7, 1024), (7, 513), (10, 24), (11, 1024), (13, 8)])
+def test_host_pointer_table_api(fecc, oracle, L, S):
+    """MFA_NTT / EncodeReedSolomon body through the reference's T** call surface (ntt.cpp:382, RS.cpp:41-63)."""
+    N = 1 << L
+    a = ol.fill_B(oracle, N, S)
+    b = a.copy(); fecc.MFA_NTT(b, N, S, False); assert np.array_equal(b, ol.o_ntt(oracle, a, False))
+    b = a.copy(); fecc.MFA_NTT(b, N, S, True);  assert np.array_equal(b, ol.o_ntt(oracle, a, True))
+    b = a.copy(); fecc.EncodeReedSolomon_body(b, N, S); assert np.array_equal(b, ol.o_encode(oracle, a))
+
+
+def test_host_scattered_blocks(fecc, oracle):
+    """Blocks at arbitrary addresses, in permuted order (the reference leaves its own table permuted)."""
+    N, S = 64, 12
+    a = ol.fill_B(oracle, N, S)
+    rng = np.random.default_rng(5)
+    pool = np.zeros((N * 3, S), dtype=np.uint32)
+    rows = rng.permutation(N * 3)[:N]
+    blocks = []
+    for i in range(N):
+        pool[rows[i]] = a[i]; blocks.append(pool[rows[i]])
+    fecc.EncodeReedSolomon_body(blocks, N, S)
+    want = ol.o_encode(oracle, a)
+    for i in range(N):
+        assert np.array_equal(blocks[i], want[i])
+
+
+def test_reference_vectors(fecc):
+    for key in V.files:
+        if not key.startswith("in_"):
+            continue
+        L, S = map(int, key.split("_")[1:])
+        x = V[key]
+        assert np.array_equal(dev_ntt(fecc, x, False), V["ntt0_%d_%d" % (L, S)]), key
+        assert np.array_equal(dev_ntt(fecc, x, True), V["ntt1_%d_%d" % (L, S)]), key
+        assert np.array_equal(dev_encode(fecc, x), V["enc_%d_%d" % (L, S)]), key
+
+
+def test_tiny_known_answers(fecc):
+    a = np.array([[1], [2], [3], [4]], dtype=np.uint32)
+    assert dev_ntt(fecc, a, False).ravel().tolist() == G["ntt4_fwd"]
+    assert dev_ntt(fecc, a, True).ravel().tolist() == G["ntt4_inv"]
+    a = np.arange(1, 9, dtype=np.uint32).reshape(8, 1)
+    assert dev_ntt(fecc, a, False).ravel().tolist() == G["ntt8_fwd"]
+
+
+def test_non_canonical_inputs_are_taken_mod_p(fecc, oracle):
+    """Inputs >= P (the reference requires < P, GF(p).cpp:47): we reduce them, outputs stay canonical."""
+    N, S = 512, 8
+    rng = np.random.default_rng(11)
+    raw = rng.integers(0, 1 << 32, size=(N, S), dtype=np.uint64).astype(np.uint32)
+    raw[0, 0] = 0xFFFFFFFF; raw[1, 0] = P; raw[2, 0] = P + 1
+    red = (raw.astype(np.uint64) % P).astype(np.uint32)
+    out = dev_encode(fecc, raw)
+    assert np.array_equal(out, ol.o_encode(oracle, red)) and int(out.max()) < P
+
+
+@pytest.mark.parametrize("L", [7, 10, 11, 12, 16])
+def test_hash_goldens_4096_byte_blocks(fecc, oracle, L):
+    """`ntt n L 4096` and `rs L 4096` hashes recorded from the unmodified reference."""
+    N = 1 << L
+    a = ol.fill_A(oracle, N, 1024)
+    h0, h1 = G["ntt_fillA_4096B"][str(L)]
+    assert ol.ohash(oracle, a) == h0
+    assert ol.ohash(oracle, dev_ntt(fecc, a, False)) == h1
+    for l, s, e0, e1 in G["encode_fillA"]:
+        if l == L and s == 1024:
+            assert ol.ohash(oracle, dev_encode(fecc, a)) == e1
+
+
+def test_published_hash_pair(fecc, oracle):
+    """Benchmarks.md:491-507."""
+    a = ol.fill_A(oracle, 1 << 20, 8)
+    assert ol.ohash(oracle, a) == G["published_ntt_2p20_32B"][0]
+    assert ol.ohash(oracle, dev_ntt(fecc, a, False)) == G["published_ntt_2p20_32B"][1]
+
+
+def test_headline_config_encode_goldens(fecc, oracle):
+    """BASELINE configs[1]: (n,k)=(2^20,2^19), 4096-byte blocks.  Parity hash must equal the reference's."""
+    import torch
+    N, S = 1 << 19, 1024
+    for fill, key in ((ol.fill_A, "encode_fillA"), (ol.fill_B, "encode_fillB")):
+        _, _, h0, h1 = [g for g in G[key] if g[0] == 19][0]
+        a = fill(oracle, N, S)
+        assert ol.ohash(oracle, a) == h0
+        t = to_dev(a); del a
+        fecc.rs_encode_dev(t)
+        out = to_host(t)
+        assert int(out.max()) < P
+        assert ol.ohash(oracle, out) == h1
+        del t, out
+        torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("L", [19, 20])
+def test_full_size_ntt_goldens_and_roundtrip(fecc, oracle, L):
+    """BASELINE configs[4] end points; iNTT(NTT(x)) == N*x mod P checked on the device for all 2^(L+10) words."""
+    import torch
+    N, S = 1 << L, 1024
+    h0, h1 = G["ntt_fillA_4096B"][str(L)]
+    a = ol.fill_A(oracle, N, S)
+    assert ol.ohash(oracle, a) == h0
+    t = to_dev(a); del a
+    orig = t.clone()
+    fecc.ntt_dev(t, False)
+    assert ol.ohash(oracle, to_host(t)) == h1
+    fecc.ntt_dev(t, True)
+    for lo in range(0, N, 1 << 16):                            # chunked to bound temporary memory
+        want = (orig[lo:lo + (1 << 16)].long() & 0xFFFFFFFF) * N % P
+        got = t[lo:lo + (1 << 16)].long() & 0xFFFFFFFF
+        assert bool((want == got).all())
+    del t, orig
+    torch.cuda.empty_cache()
+
+
+def test_full_size_encode_linearity(fecc, oracle):
+    """encode(a + b) == encode(a) + encode(b) (mod P) at N = 2^19 x 4096 B."""
+    import torch
+    N, S = 1 << 19, 1024
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    a = torch.randint(0, P, (N, S), device="cuda", generator=g, dtype=torch.int64)
+    b = torch.randint(0, P, (N, S), device="cuda", generator=g, dtype=torch.int64)
+    s = ((a + b) % P).to(torch.int32); a = a.to(torch.int32); b = b.to(torch.int32)
+    for t in (a, b, s):
+        fecc.rs_encode_dev(t)
+    ok = True
+    for lo in range(0, N, 1 << 16):
+        sl = slice(lo, lo + (1 << 16))
+        ok &= bool(((((a[sl].long() & 0xFFFFFFFF) + (b[sl].long() & 0xFFFFFFFF)) % P) == (s[sl].long() & 0xFFFFFFFF)).all())
+    assert ok
+
+
+def test_argument_validation(fecc):
+    a = np.zeros((3, 4), dtype=np.uint32)
+    with pytest.raises(fecc.FastEccError) as e:
+        fecc.MFA_NTT(a, 3, 4, False)
+    assert e.value.code == -1
+    import torch
+    t = torch.zeros((1 << 20, 4), dtype=torch.int32, device="cuda")
+    with pytest.raises(fecc.FastEccError) as e:                 # rs 20: rejected (the reference computes garbage, GF(p).cpp:274)
+        fecc.rs_encode_dev(t)
+    assert e.value.code == -1
+    fecc.ntt_dev(t, False)                                      # but a 2^20 NTT is legal
