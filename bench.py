@@ -125,7 +125,7 @@ def cpu_encode_runner(log_n, size_words):
         tab = (ctypes.c_void_p * N)()                   # T** data, RS.cpp:31-33; left permuted between steps like the reference leaves it
         for i in range(N):
             tab[i] = buf.ctypes.data + i * size_words * 4
-        return (lambda: r.ref_rs_encode(tab, N, size_words)), "reference", int(r.ref_num_threads()), \
+        return (lambda _keep=buf: r.ref_rs_encode(tab, N, size_words)), "reference", int(r.ref_num_threads()), \
             "unmodified FastECC templates, %s+OpenMP build (oracle/_ref)" % r.ref_build_flavour().decode()
     o = load_oracle_port()
     return (lambda: o.oracle_rs_encode(buf.ctypes.data, N, size_words)), "port", int(o.oracle_num_threads()), "oracle/gfp_oracle.c (plain C port, OpenMP)"
