@@ -57,7 +57,7 @@ struct PassParams {
     uint32_t nsets;                              // number of independent row sets
     uint32_t nstrips;                            // ceil(s4 / Q)
     uint32_t strips_per_item;                    // consecutive strips of one set handled by one CTA visit
-    unsigned long long src_set_stride, src_row_stride, dst_set_stride, dst_row_stride;   // in rows
+    uint32_t src_set_stride, src_row_stride, dst_set_stride, dst_row_stride;             // in rows
     uint32_t nxf;                                // 1, or 2 = two transforms back to back on the same tile
     Xform    xf[2];
     uint32_t prescale;                           // multiply every input word by the constant below (1/N)
@@ -90,12 +90,16 @@ FECC_HD uint32_t tile_chunk(uint32_t p, uint32_t q, uint32_t qlog, uint32_t pari
     return (p << qlog) | q;
 }
 
-// number of rounds and per-round (lb, bmin) of a size-2^LR transform
+// Rounds of a size-2^LR transform: nr = ceil(LR/4).  Round 0 executes the first rem = LR - 4(nr-1) stages (bits
+// [0, rem)) with bits 0..3 in-thread; round k >= 1 executes the four stages of bits [lb, lb+4), lb = rem + 4(k-1).
+// Putting the short round first leaves a full four-stage round at the end of the tile, which is the compute that
+// hides the next tile's cp.async loads (ntt_pass.cu).
 FECC_HD uint32_t num_rounds(uint32_t LR) { return (LR + 3) >> 2; }
-FECC_HD void round_bits(uint32_t LR, uint32_t k, uint32_t& lb, uint32_t& bmin)
+FECC_HD void round_bits(uint32_t LR, uint32_t k, uint32_t& lb, uint32_t& blo, uint32_t& bhi)
 {
-    bmin = 4 * k;
-    lb = (bmin + 4 <= LR) ? bmin : LR - 4;
+    const uint32_t rem = LR - 4 * (num_rounds(LR) - 1);
+    if (k == 0) { lb = 0; blo = 0; bhi = rem; }
+    else        { lb = rem + 4 * (k - 1); blo = lb; bhi = lb + 4; }
 }
 
 // exponent of heap entry idx (1 <= idx < R) of the stage table
@@ -120,9 +124,11 @@ FECC_HD void bfly4(uint4& a, uint4& b, const uint4& w, uint32_t zero)
     v = gf::mul(b.w, w.x, w.y, w.z, zero); b.w = gf::subl(a.w, v); a.w = gf::addl(a.w, v);
 }
 
+FECC_HD uint4 canon4(uint4 v) { v.x = gf::canon(v.x); v.y = gf::canon(v.y); v.z = gf::canon(v.z); v.w = gf::canon(v.w); return v; }
+
 // Slot bookkeeping of one thread in one round.
 struct RoundCtx {
-    uint32_t lb, bmin;        // bits [lb, lb+4) are in-thread; stages for bits >= bmin are executed
+    uint32_t lb, blo, bhi;    // bits [lb, lb+4) are in-thread; the stages of bits [blo, bhi) are executed
     uint32_t jbase;           // slot index with the in-thread bits zero
     uint32_t jlow;            // low lb bits of j (= low lb bits of every slot of this thread)
 };
@@ -130,7 +136,7 @@ struct RoundCtx {
 FECC_HD RoundCtx make_round(uint32_t LR, uint32_t k, uint32_t j)
 {
     RoundCtx c;
-    round_bits(LR, k, c.lb, c.bmin);
+    round_bits(LR, k, c.lb, c.blo, c.bhi);
     c.jlow  = j & ((1u << c.lb) - 1u);
     c.jbase = ((j >> c.lb) << (c.lb + 4)) | c.jlow;
     return c;
@@ -138,12 +144,12 @@ FECC_HD RoundCtx make_round(uint32_t LR, uint32_t k, uint32_t j)
 
 // The register-resident part of a round: up to four radix-2 DIT stages on the thread's 16 slots x 4 words.
 // tw points at the heap-ordered stage table of the current transform (shared memory on the device).
-FECC_HD void round_compute(uint4 (&x)[16], const RoundCtx& c, uint32_t LR, const uint4* tw, uint32_t zero)
+FECC_HD void round_compute(uint4 (&x)[16], const RoundCtx& c, const uint4* tw, uint32_t zero)
 {
 #pragma unroll
     for (int beta = 0; beta < 4; ++beta) {
         const uint32_t b = c.lb + beta;
-        if (b >= c.bmin && b < LR) {
+        if (b >= c.blo && b < c.bhi) {
             const uint4* twb = tw + (1u << b) + c.jlow;
 #pragma unroll
             for (int m = 0; m < (1 << beta); ++m) {
@@ -153,6 +159,58 @@ FECC_HD void round_compute(uint4 (&x)[16], const RoundCtx& c, uint32_t LR, const
                     const int i0 = (hi << (beta + 1)) | m;
                     const int i1 = i0 | (1 << beta);
                     bfly4(x[i0], x[i1], w, zero);
+                }
+            }
+        }
+    }
+}
+
+// Round 0 of a PLAIN transform (no input twist): the twiddle of every pair whose low bits are zero is 1, which is
+// known at compile time because lb = 0 makes the table index depend on the in-thread index only.  Those
+// butterflies need no product: the b operand is merely brought to [0,P) (two ALU instructions) so that the lazy
+// add/sub stay closed.  The uniform pre-scale by 1/N (RS.cpp:51,54) is folded into stage 0, whose 8 butterflies
+// then cost two products each instead of one product plus two pre-scale products.
+FECC_HD void round0_plain(uint4 (&x)[16], const RoundCtx& c, const uint4* tw, bool PRESCALE, uint32_t pw, uint32_t pwhi, uint32_t pwlo, uint32_t zero)
+{
+    const uint4 cw = {pw, pwhi, pwlo, 0};
+#pragma unroll
+    for (int hi = 0; hi < 8; ++hi) {                       // stage 0: all twiddles are 1
+        uint4& a = x[2 * hi]; uint4& b = x[2 * hi + 1];
+        if (PRESCALE) {
+            a.x = gf::mul(a.x, cw.x, cw.y, cw.z, zero); a.y = gf::mul(a.y, cw.x, cw.y, cw.z, zero);
+            a.z = gf::mul(a.z, cw.x, cw.y, cw.z, zero); a.w = gf::mul(a.w, cw.x, cw.y, cw.z, zero);
+            b.x = gf::mul(b.x, cw.x, cw.y, cw.z, zero); b.y = gf::mul(b.y, cw.x, cw.y, cw.z, zero);
+            b.z = gf::mul(b.z, cw.x, cw.y, cw.z, zero); b.w = gf::mul(b.w, cw.x, cw.y, cw.z, zero);
+        } else {
+            b = canon4(b);
+        }
+        uint32_t t;
+        t = b.x; b.x = gf::subl(a.x, t); a.x = gf::addl(a.x, t);
+        t = b.y; b.y = gf::subl(a.y, t); a.y = gf::addl(a.y, t);
+        t = b.z; b.z = gf::subl(a.z, t); a.z = gf::addl(a.z, t);
+        t = b.w; b.w = gf::subl(a.w, t); a.w = gf::addl(a.w, t);
+    }
+#pragma unroll
+    for (int beta = 1; beta < 4; ++beta) {
+        if ((uint32_t)beta < c.bhi) {
+            const uint4* twb = tw + (1u << beta);
+#pragma unroll
+            for (int m = 0; m < (1 << beta); ++m) {
+                uint4 w = {0, 0, 0, 0};
+                if (m) w = twb[m];
+#pragma unroll
+                for (int hi = 0; hi < (8 >> beta); ++hi) {
+                    const int i0 = (hi << (beta + 1)) | m;
+                    const int i1 = i0 | (1 << beta);
+                    if (m) {
+                        bfly4(x[i0], x[i1], w, zero);
+                    } else {
+                        uint4& a = x[i0]; uint4 b = canon4(x[i1]);
+                        x[i1].x = gf::subl(a.x, b.x); a.x = gf::addl(a.x, b.x);
+                        x[i1].y = gf::subl(a.y, b.y); a.y = gf::addl(a.y, b.y);
+                        x[i1].z = gf::subl(a.z, b.z); a.z = gf::addl(a.z, b.z);
+                        x[i1].w = gf::subl(a.w, b.w); a.w = gf::addl(a.w, b.w);
+                    }
                 }
             }
         }
@@ -179,18 +237,16 @@ FECC_HD void prescale16(uint4 (&x)[16], uint32_t w, uint32_t whi, uint32_t wlo, 
     }
 }
 
-FECC_HD uint4 canon4(uint4 v) { v.x = gf::canon(v.x); v.y = gf::canon(v.y); v.z = gf::canon(v.z); v.w = gf::canon(v.w); return v; }
-
-// Global row (in rows, relative to the buffer start) that feeds physical tile row p of the FIRST transform:
-// slot p holds DIT input element bitrev(p).
-FECC_HD unsigned long long src_row_of(const PassParams& P, uint32_t set, uint32_t p)
+// Row (relative to the buffer start) that feeds physical tile row p of the FIRST transform: slot p holds DIT
+// input element bitrev(p).  Row and chunk indices are 32-bit: api.cu rejects buffers of 2^32 chunks (64 GiB) or more.
+FECC_HD uint32_t src_row_of(const PassParams& P, uint32_t set, uint32_t p)
 {
-    return (unsigned long long)set * P.src_set_stride + (unsigned long long)bitrev(p, P.log_r) * P.src_row_stride;
+    return set * P.src_set_stride + bitrev(p, P.log_r) * P.src_row_stride;
 }
-// Global row that receives output element r (slot r of the LAST transform)
-FECC_HD unsigned long long dst_row_of(const PassParams& P, uint32_t set, uint32_t r)
+// Row that receives output element r (slot r of the LAST transform)
+FECC_HD uint32_t dst_row_of(const PassParams& P, uint32_t set, uint32_t r)
 {
-    return (unsigned long long)set * P.dst_set_stride + (unsigned long long)r * P.dst_row_stride;
+    return set * P.dst_set_stride + r * P.dst_row_stride;
 }
 
 } // namespace fecc
@@ -202,68 +258,109 @@ FECC_HD unsigned long long dst_row_of(const PassParams& P, uint32_t set, uint32_
 // ---------------------------------------------------------------------------------------------------------------
 namespace fecc {
 
+// P.xf[xfi] with a runtime xfi would make the compiler copy the kernel parameters to local memory
+FECC_HD Xform get_xf(const PassParams& P, uint32_t xfi)
+{
+    Xform x;
+    x.z  = xfi ? P.xf[1].z  : P.xf[0].z;
+    x.t0 = xfi ? P.xf[1].t0 : P.xf[0].t0;
+    x.t1 = xfi ? P.xf[1].t1 : P.xf[0].t1;
+    return x;
+}
+
 struct ThreadPos { uint32_t q, j, qlog, Q; };
 FECC_HD ThreadPos thread_pos(const PassParams& P, uint32_t tid)
 {
     ThreadPos t; t.qlog = 12 - P.log_r; t.Q = 1u << t.qlog; t.q = tid & (t.Q - 1); t.j = tid >> t.qlog; return t;
 }
 
-// Fill the heap-ordered stage table of transform xfi for row set `set` from the global power table.
+FECC_HD void copy16(uint4* dst_smem, const uint4* src_gmem)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t s = (uint32_t)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(src_gmem));
+#else
+    *dst_smem = *src_gmem;
+#endif
+}
+
+// Gather the heap-ordered stage table of transform xfi for row set `set` from the global power table (cp.async).
 FECC_HD void build_table(const PassParams& P, uint32_t xfi, uint32_t set, uint32_t tid, uint4* tw_s)
 {
     const uint32_t R = 1u << P.log_r;
-    const uint32_t z = P.xf[xfi].z;
-    const uint32_t t = (P.xf[xfi].t0 + set * P.xf[xfi].t1) & (gf::M - 1);
+    const Xform xf = get_xf(P, xfi);
+    const uint32_t z = xf.z;
+    const uint32_t t = (xf.t0 + set * xf.t1) & (gf::M - 1);
     for (uint32_t idx = tid; idx < R; idx += kThreads)
-        if (idx) tw_s[idx] = P.tw[table_exponent(idx, P.log_r, z, t)];
+        if (idx) copy16(tw_s + idx, P.tw + table_exponent(idx, P.log_r, z, t));
 }
 
-// One round of transform xfi on the thread's 16 slots.  The last round of the last transform stores to global
-// memory (output element r -> row dst_row_of(r)); every other round writes back to the tile in place.
-FECC_HD void run_round(const PassParams& P, uint32_t xfi, uint32_t k, uint32_t tid, uint32_t set, uint32_t strip,
-                       uint4* tile, const uint4* tw_s, uint32_t zero)
+// Issue the (asynchronous) loads of tile (set, strip): thread tid moves chunks c = tid + 256*m, m = 0..15.
+FECC_HD void load_tile(const PassParams& P, uint32_t set, uint32_t strip, uint32_t tid, uint4* tile)
 {
-    const uint32_t LR = P.log_r;
-    const ThreadPos tp = thread_pos(P, tid);
-    const uint32_t gcol = strip * tp.Q + tp.q;                 // chunk column inside the row
-    if (gcol >= P.s4) return;                                  // partial last strip: nothing to do for this thread
-    const RoundCtx c = make_round(LR, k, tp.j);
-    const bool first = (xfi == 0 && k == 0);
-    const bool last  = (xfi + 1 == P.nxf) && (k + 1 == num_rounds(LR));
-
-    uint4    x[16];
-    uint32_t off[16];
+    const uint32_t qlog = 12 - P.log_r, Q = 1u << qlog;
+    const uint4* src4 = reinterpret_cast<const uint4*>(P.src);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { off[i] = slot_chunk(c, i, tp.q, LR, tp.qlog, xfi, P.parity); x[i] = tile[off[i]]; }
-
-    if (first && P.prescale) prescale16(x, P.pw, P.pwhi, P.pwlo, zero);
-    round_compute(x, c, LR, tw_s, zero);
-
-    if (!last) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) tile[off[i]] = x[i];
-    } else {
-        uint4* dst4 = reinterpret_cast<uint4*>(P.dst);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const uint32_t r = c.jbase | ((uint32_t)i << c.lb);
-            const unsigned long long row = dst_row_of(P, set, r);
-            dst4[row * P.pitch4 + gcol] = P.canonical_out ? canon4(x[i]) : x[i];
-        }
+    for (int m = 0; m < 16; ++m) {
+        const uint32_t c = tid + (uint32_t)kThreads * m;
+        const uint32_t p = c >> qlog, qq = c & (Q - 1);
+        const uint32_t gcol = strip * Q + qq;
+        if (gcol < P.s4) copy16(tile + tile_chunk(p, qq, qlog, P.parity), src4 + ((size_t)(src_row_of(P, set, p) * P.pitch4 + gcol)));
     }
 }
 
-// Which global chunk goes to which tile chunk: thread tid moves chunks c = tid + 256*m, m = 0..15.
-FECC_HD bool load_map(const PassParams& P, uint32_t set, uint32_t strip, uint32_t tid, int m,
-                      unsigned long long& src_chunk, uint32_t& tile_idx)
+struct RoundRegs { uint4 x[16]; };
+
+FECC_HD bool thread_active(const PassParams& P, uint32_t tid, uint32_t strip)
 {
-    const uint32_t qlog = 12 - P.log_r, Q = 1u << qlog;
-    const uint32_t c = tid + (uint32_t)kThreads * m;
-    const uint32_t p = c >> qlog, qq = c & (Q - 1);
-    const uint32_t gcol = strip * Q + qq;
-    tile_idx  = tile_chunk(p, qq, qlog, P.parity);
-    src_chunk = src_row_of(P, set, p) * P.pitch4 + gcol;
-    return gcol < P.s4;
+    const ThreadPos tp = thread_pos(P, tid);
+    return strip * tp.Q + tp.q < P.s4;                          // partial last strip: column chunk beyond the row
+}
+
+// (a) read the thread's 16 slots of round k of transform xfi
+FECC_HD void round_read(const PassParams& P, uint32_t xfi, uint32_t k, uint32_t tid, const uint4* tile, RoundRegs& r)
+{
+    const ThreadPos tp = thread_pos(P, tid);
+    const RoundCtx c = make_round(P.log_r, k, tp.j);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r.x[i] = tile[slot_chunk(c, i, tp.q, P.log_r, tp.qlog, xfi, P.parity)];
+}
+
+// (b) the butterflies
+FECC_HD void round_math(const PassParams& P, uint32_t xfi, uint32_t k, uint32_t tid, uint32_t set, const uint4* tw_s, RoundRegs& r, uint32_t zero)
+{
+    const ThreadPos tp = thread_pos(P, tid);
+    const RoundCtx c = make_round(P.log_r, k, tp.j);
+    const bool first = (xfi == 0 && k == 0);
+    const Xform xf = get_xf(P, xfi);
+    const bool plain = ((xf.t0 + set * xf.t1) & (gf::M - 1)) == 0;
+    if (k == 0 && plain) {
+        round0_plain(r.x, c, tw_s, first && P.prescale, P.pw, P.pwhi, P.pwlo, zero);
+    } else {
+        if (first && P.prescale) prescale16(r.x, P.pw, P.pwhi, P.pwlo, zero);
+        round_compute(r.x, c, tw_s, zero);
+    }
+}
+
+// (c) write back in place, or (last round of the last transform) store output element r to its global row
+FECC_HD void round_write_tile(const PassParams& P, uint32_t xfi, uint32_t k, uint32_t tid, uint4* tile, const RoundRegs& r)
+{
+    const ThreadPos tp = thread_pos(P, tid);
+    const RoundCtx c = make_round(P.log_r, k, tp.j);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) tile[slot_chunk(c, i, tp.q, P.log_r, tp.qlog, xfi, P.parity)] = r.x[i];
+}
+FECC_HD void round_write_global(const PassParams& P, uint32_t k, uint32_t tid, uint32_t set, uint32_t strip, const RoundRegs& r)
+{
+    const ThreadPos tp = thread_pos(P, tid);
+    const RoundCtx c = make_round(P.log_r, k, tp.j);
+    const uint32_t gcol = strip * tp.Q + tp.q;
+    uint4* dst4 = reinterpret_cast<uint4*>(P.dst);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const uint32_t row = dst_row_of(P, set, c.jbase | ((uint32_t)i << c.lb));
+        dst4[(size_t)(row * P.pitch4 + gcol)] = P.canonical_out ? canon4(r.x[i]) : r.x[i];
+    }
 }
 
 } // namespace fecc

@@ -66,7 +66,7 @@ inline std::vector<PassParams> plan_ntt(const Buffers& b, size_t N, bool inverse
         return v;
     }
     const uint32_t L1 = (LN + 1) / 2, L2 = LN - L1;
-    const unsigned long long N1 = 1ull << L1, N2 = 1ull << L2;
+    const uint32_t N1 = 1u << L1, N2 = 1u << L2;
     PassParams a = base_pass(b, L1);
     a.src = b.x; a.dst = b.y; a.nsets = (uint32_t)N2;
     a.src_set_stride = 1;  a.src_row_stride = N2;
@@ -104,7 +104,7 @@ inline std::vector<PassParams> plan_encode(const Buffers& b, size_t N)
         return v;
     }
     const uint32_t L1 = (LN + 1) / 2, L2 = LN - L1;
-    const unsigned long long N1 = 1ull << L1, N2 = 1ull << L2;
+    const uint32_t N1 = 1u << L1, N2 = 1u << L2;
     PassParams a = base_pass(b, L1);
     a.src = b.x; a.dst = b.x; a.nsets = (uint32_t)N2;
     a.src_set_stride = a.dst_set_stride = 1; a.src_row_stride = a.dst_row_stride = N2;

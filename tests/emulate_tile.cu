@@ -13,31 +13,36 @@ using namespace fecc;
 
 static void emulate_pass(const PassParams& P)
 {
-    std::vector<uint4> tile(kTileChunks), tw0(1u << P.log_r), tw1(1u << P.log_r);
+    const uint32_t R = 1u << P.log_r;
+    std::vector<uint4> tile(kTileChunks), tabs(2 * R);
     const uint32_t groups = (P.nstrips + P.strips_per_item - 1) / P.strips_per_item;
     const uint32_t nitems = P.nsets * groups;
     const uint32_t nrounds = num_rounds(P.log_r);
-    const uint4* src4 = reinterpret_cast<const uint4*>(P.src);
+    std::vector<RoundRegs> regs(kThreads);
     for (uint32_t item = 0; item < nitems; ++item) {
         const uint32_t set = item / groups, sg = item - set * groups;
         const uint32_t strip0 = sg * P.strips_per_item;
         const uint32_t strip1 = std::min(strip0 + P.strips_per_item, P.nstrips);
         for (uint32_t strip = strip0; strip < strip1; ++strip) {
             for (auto& c : tile) c = make_uint4(0xDEADBEEF, 0xDEADBEEF, 0xDEADBEEF, 0xDEADBEEF);
-            for (uint32_t tid = 0; tid < kThreads; ++tid)
-                for (int m = 0; m < 16; ++m) {
-                    unsigned long long sc; uint32_t ti;
-                    if (load_map(P, set, strip, tid, m, sc, ti)) tile[ti] = src4[sc];
-                }
+            for (uint32_t tid = 0; tid < kThreads; ++tid) load_tile(P, set, strip, tid, tile.data());
             if (strip == strip0)
-                for (uint32_t tid = 0; tid < kThreads; ++tid) {
-                    build_table(P, 0, set, tid, tw0.data());
-                    if (P.nxf == 2) build_table(P, 1, set, tid, tw1.data());
-                }
+                for (uint32_t tid = 0; tid < kThreads; ++tid)
+                    for (uint32_t x = 0; x < P.nxf; ++x) build_table(P, x, set, tid, tabs.data() + x * R);
             for (uint32_t xfi = 0; xfi < P.nxf; ++xfi)
-                for (uint32_t k = 0; k < nrounds; ++k)
-                    for (uint32_t tid = 0; tid < kThreads; ++tid)
-                        run_round(P, xfi, k, tid, set, strip, tile.data(), xfi ? tw1.data() : tw0.data(), 0);
+                for (uint32_t k = 0; k < nrounds; ++k) {
+                    const bool last = (xfi + 1 == P.nxf) && (k + 1 == nrounds);
+                    for (uint32_t tid = 0; tid < kThreads; ++tid) {
+                        if (!thread_active(P, tid, strip)) continue;
+                        round_read(P, xfi, k, tid, tile.data(), regs[tid]);
+                    }
+                    for (uint32_t tid = 0; tid < kThreads; ++tid) {
+                        if (!thread_active(P, tid, strip)) continue;
+                        round_math(P, xfi, k, tid, set, tabs.data() + xfi * R, regs[tid], 0);
+                        if (last) round_write_global(P, k, tid, set, strip, regs[tid]);
+                        else      round_write_tile(P, xfi, k, tid, tile.data(), regs[tid]);
+                    }
+                }
         }
     }
 }
