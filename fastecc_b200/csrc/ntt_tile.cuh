@@ -146,14 +146,16 @@ FECC_HD RoundCtx make_round(uint32_t LR, uint32_t k, uint32_t j)
 // tw points at the heap-ordered stage table of the current transform (shared memory on the device).
 FECC_HD void round_compute(uint4 (&x)[16], const RoundCtx& c, const uint4* tw, uint32_t zero)
 {
+    const uint32_t sb = 1u << c.lb;                     // table stride between consecutive in-thread twiddles
+    const uint4* tb = tw + c.jlow;
 #pragma unroll
     for (int beta = 0; beta < 4; ++beta) {
         const uint32_t b = c.lb + beta;
         if (b >= c.blo && b < c.bhi) {
-            const uint4* twb = tw + (1u << b) + c.jlow;
+            const uint4* twp = tb + (sb << beta);       // heap entry 2^b + jlow (+ m * 2^lb)
 #pragma unroll
             for (int m = 0; m < (1 << beta); ++m) {
-                const uint4 w = twb[(uint32_t)m << c.lb];
+                const uint4 w = *twp; twp += sb;
 #pragma unroll
                 for (int hi = 0; hi < (8 >> beta); ++hi) {
                     const int i0 = (hi << (beta + 1)) | m;
@@ -217,14 +219,9 @@ FECC_HD void round0_plain(uint4 (&x)[16], const RoundCtx& c, const uint4* tw, bo
     }
 }
 
-// Where the thread's slot i lives in the tile buffer.  `brev` selects the bit-reversed placement used by the
-// second transform of a fused tile (its DIT input index bitrev(r) is the first transform's output slot).
-FECC_HD uint32_t slot_chunk(const RoundCtx& c, int i, uint32_t q, uint32_t LR, uint32_t qlog, uint32_t brev, uint32_t parity)
-{
-    uint32_t r = c.jbase | ((uint32_t)i << c.lb);
-    uint32_t p = brev ? bitrev(r, LR) : r;
-    return tile_chunk(p, q, qlog, parity);
-}
+// Compile-time helpers for the unrolled slot loops
+FECC_HD constexpr uint32_t par4(int i)  { return (0x6996u >> i) & 1u; }                                   // popcount(i) & 1
+FECC_HD constexpr int      brev4(int i) { return ((i & 1) << 3) | ((i & 2) << 1) | ((i & 4) >> 1) | ((i & 8) >> 3); }
 
 FECC_HD void prescale16(uint4 (&x)[16], uint32_t w, uint32_t whi, uint32_t wlo, uint32_t zero)
 {
@@ -235,18 +232,6 @@ FECC_HD void prescale16(uint4 (&x)[16], uint32_t w, uint32_t whi, uint32_t wlo, 
         x[i].z = gf::mul(x[i].z, w, whi, wlo, zero);
         x[i].w = gf::mul(x[i].w, w, whi, wlo, zero);
     }
-}
-
-// Row (relative to the buffer start) that feeds physical tile row p of the FIRST transform: slot p holds DIT
-// input element bitrev(p).  Row and chunk indices are 32-bit: api.cu rejects buffers of 2^32 chunks (64 GiB) or more.
-FECC_HD uint32_t src_row_of(const PassParams& P, uint32_t set, uint32_t p)
-{
-    return set * P.src_set_stride + bitrev(p, P.log_r) * P.src_row_stride;
-}
-// Row that receives output element r (slot r of the LAST transform)
-FECC_HD uint32_t dst_row_of(const PassParams& P, uint32_t set, uint32_t r)
-{
-    return set * P.dst_set_stride + r * P.dst_row_stride;
 }
 
 } // namespace fecc
@@ -295,17 +280,25 @@ FECC_HD void build_table(const PassParams& P, uint32_t xfi, uint32_t set, uint32
         if (idx) copy16(tw_s + idx, P.tw + table_exponent(idx, P.log_r, z, t));
 }
 
-// Issue the (asynchronous) loads of tile (set, strip): thread tid moves chunks c = tid + 256*m, m = 0..15.
+// Issue the (asynchronous) loads of tile (set, strip).  Thread tid moves the 16 chunks c = tid + 256*m: tile row
+// p = p0 + m*2^(LR-4), whose source row is bitrev(p) = bitrev(p0) + brev4(m) -- sixteen consecutive source rows,
+// walked with one pointer increment each.
 FECC_HD void load_tile(const PassParams& P, uint32_t set, uint32_t strip, uint32_t tid, uint4* tile)
 {
-    const uint32_t qlog = 12 - P.log_r, Q = 1u << qlog;
-    const uint4* src4 = reinterpret_cast<const uint4*>(P.src);
+    const uint32_t LR = P.log_r, qlog = 12 - LR, Q = 1u << qlog;
+    const uint32_t p0 = tid >> qlog, qq = tid & (Q - 1);
+    const uint32_t gcol = strip * Q + qq;
+    if (gcol >= P.s4) return;
+    const uint32_t row0 = set * P.src_set_stride + bitrev(p0, LR) * P.src_row_stride;
+    const uint4* g = reinterpret_cast<const uint4*>(P.src) + ((size_t)row0 * P.pitch4 + gcol);
+    const size_t gstep = (size_t)P.src_row_stride * P.pitch4;
+    uint32_t cbase = (p0 << qlog) | qq;
+    if (P.parity) cbase ^= (popc32(p0 >> 1) & 1u) << qlog;
+    const uint32_t pbit = P.parity ? (1u << qlog) : 0u;
 #pragma unroll
-    for (int m = 0; m < 16; ++m) {
-        const uint32_t c = tid + (uint32_t)kThreads * m;
-        const uint32_t p = c >> qlog, qq = c & (Q - 1);
-        const uint32_t gcol = strip * Q + qq;
-        if (gcol < P.s4) copy16(tile + tile_chunk(p, qq, qlog, P.parity), src4 + ((size_t)(src_row_of(P, set, p) * P.pitch4 + gcol)));
+    for (int k = 0; k < 16; ++k) {                          // k = brev4(m): k-th consecutive source row
+        copy16(tile + ((cbase + 256u * (uint32_t)brev4(k)) ^ (par4(k) ? pbit : 0u)), g);
+        g += gstep;
     }
 }
 
@@ -317,13 +310,38 @@ FECC_HD bool thread_active(const PassParams& P, uint32_t tid, uint32_t strip)
     return strip * tp.Q + tp.q < P.s4;                          // partial last strip: column chunk beyond the row
 }
 
+// Tile chunk of the thread's slot i in round c:  physical row = slot (first transform) or bitrev(slot) (second
+// transform of a fused tile), rows of a pair swapped by popcount parity when P.parity.  All variants reduce to
+// "base + i*step" (or base ^ const) so that a round spends one ALU instruction per 16-byte access.
+#define FECC_SLOT_LOOP(ACCESS)                                                                                     \
+    if (P.parity) {                    /* identity placement only: plan.h never combines parity with a fused tile */ \
+        if (c.lb == 0) {                                                                                           \
+            const uint32_t B = ((tp.j << 6) | tp.q) ^ ((popc32(tp.j) & 1u) << 2);                                  \
+            _Pragma("unroll") for (int i = 0; i < 16; ++i) { const uint32_t a = B ^ (uint32_t)((i ^ (int)par4(i >> 1)) << 2); ACCESS(i, a); } \
+        } else {                                                                                                   \
+            uint32_t a0 = ((c.jbase ^ (popc32(c.jbase >> 1) & 1u)) << 2) | tp.q;                                   \
+            const uint32_t step = 4u << c.lb;                                                                      \
+            _Pragma("unroll") for (int i = 0; i < 16; ++i) { const uint32_t a = a0 ^ (par4(i) << 2); ACCESS(i, a); a0 += step; } \
+        }                                                                                                          \
+    } else if (xfi) {                                                                                              \
+        uint32_t a = (bitrev(c.jbase, LR) << tp.qlog) | tp.q;                                                      \
+        const uint32_t step = 1u << (LR - 4 - c.lb + tp.qlog);                                                     \
+        _Pragma("unroll") for (int k = 0; k < 16; ++k) { ACCESS(brev4(k), a); a += step; }                         \
+    } else {                                                                                                       \
+        uint32_t a = (c.jbase << tp.qlog) | tp.q;                                                                  \
+        const uint32_t step = 1u << (c.lb + tp.qlog);                                                              \
+        _Pragma("unroll") for (int i = 0; i < 16; ++i) { ACCESS(i, a); a += step; }                                \
+    }
+
 // (a) read the thread's 16 slots of round k of transform xfi
 FECC_HD void round_read(const PassParams& P, uint32_t xfi, uint32_t k, uint32_t tid, const uint4* tile, RoundRegs& r)
 {
+    const uint32_t LR = P.log_r;
     const ThreadPos tp = thread_pos(P, tid);
-    const RoundCtx c = make_round(P.log_r, k, tp.j);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) r.x[i] = tile[slot_chunk(c, i, tp.q, P.log_r, tp.qlog, xfi, P.parity)];
+    const RoundCtx c = make_round(LR, k, tp.j);
+#define FECC_RD(I, A) r.x[I] = tile[A]
+    FECC_SLOT_LOOP(FECC_RD)
+#undef FECC_RD
 }
 
 // (b) the butterflies
@@ -345,21 +363,25 @@ FECC_HD void round_math(const PassParams& P, uint32_t xfi, uint32_t k, uint32_t 
 // (c) write back in place, or (last round of the last transform) store output element r to its global row
 FECC_HD void round_write_tile(const PassParams& P, uint32_t xfi, uint32_t k, uint32_t tid, uint4* tile, const RoundRegs& r)
 {
+    const uint32_t LR = P.log_r;
     const ThreadPos tp = thread_pos(P, tid);
-    const RoundCtx c = make_round(P.log_r, k, tp.j);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) tile[slot_chunk(c, i, tp.q, P.log_r, tp.qlog, xfi, P.parity)] = r.x[i];
+    const RoundCtx c = make_round(LR, k, tp.j);
+#define FECC_WR(I, A) tile[A] = r.x[I]
+    FECC_SLOT_LOOP(FECC_WR)
+#undef FECC_WR
 }
 FECC_HD void round_write_global(const PassParams& P, uint32_t k, uint32_t tid, uint32_t set, uint32_t strip, const RoundRegs& r)
 {
     const ThreadPos tp = thread_pos(P, tid);
     const RoundCtx c = make_round(P.log_r, k, tp.j);
     const uint32_t gcol = strip * tp.Q + tp.q;
-    uint4* dst4 = reinterpret_cast<uint4*>(P.dst);
+    const uint32_t row0 = set * P.dst_set_stride + c.jbase * P.dst_row_stride;
+    uint4* g = reinterpret_cast<uint4*>(P.dst) + ((size_t)row0 * P.pitch4 + gcol);
+    const size_t gstep = ((size_t)P.dst_row_stride * P.pitch4) << c.lb;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        const uint32_t row = dst_row_of(P, set, c.jbase | ((uint32_t)i << c.lb));
-        dst4[(size_t)(row * P.pitch4 + gcol)] = P.canonical_out ? canon4(r.x[i]) : r.x[i];
+        *g = P.canonical_out ? canon4(r.x[i]) : r.x[i];
+        g += gstep;
     }
 }
 
