@@ -63,7 +63,7 @@ int check_shape(size_t N, size_t size, size_t max_log, const char* who)
 int run_aligned(Context* c, uint32_t* x, size_t N, size_t size, size_t pitch, int mode /*0 fwd,1 inv,2 encode*/, cudaStream_t st)
 {
     const uint32_t pitch4 = (uint32_t)(pitch / 4), s4 = (uint32_t)((size + 3) / 4);
-    if (N < 16) {
+    if (N < ((size_t)1 << kMinLogR)) {
         const uint32_t z = (uint32_t)(gf::M / N) * (mode == 1 ? (uint32_t)-1 : 1u) & (gf::M - 1);
         const uint32_t q = mode == 2 ? (uint32_t)(gf::M / (2 * N)) : 0;
         const gf::Tw in = gf::make_tw(gf::inv((uint32_t)N));
@@ -88,6 +88,8 @@ int run_dev(uint32_t* d, size_t N, size_t size, size_t pitch, int mode, void* st
     if (!d) return fail(FASTECC_B200_EINVAL, "%s: null device pointer", who);
     if (int rc = check_shape(N, size, mode == 2 ? FASTECC_B200_MAX_LOG_N_ENCODE : FASTECC_B200_MAX_LOG_N, who)) return rc;
     if (pitch < size) return fail(FASTECC_B200_EINVAL, "%s: pitch_words (%zu) < SIZE_words (%zu)", who, pitch, size);
+    if ((unsigned long long)N * ((pitch + 3) / 4) >= (1ull << 32))
+        return fail(FASTECC_B200_EINVAL, "%s: buffer of %zu x %zu words is 64 GiB or more (32-bit chunk indexing)", who, N, pitch);
     cudaStream_t st = (cudaStream_t)stream;
     const bool aligned = (pitch % 4 == 0) && (((uintptr_t)d) % 16 == 0);
     if (aligned) return run_aligned(c, d, N, size, pitch, mode, st);

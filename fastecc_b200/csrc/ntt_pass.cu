@@ -7,7 +7,8 @@
 //   * the tile and, when the row set changes, its twiddle table arrive by 16-byte cp.async (LDGSTS) straight into
 //     the bank-conflict-free shared-memory layout -- issued one tile AHEAD, right after the previous tile's last
 //     round has pulled its slots into registers, so the loads fly under a full four-stage round of butterflies;
-//   * ceil(LR/4) register rounds (x2 for a fused tile) separated by one block barrier each;
+//   * ceil(LR/5) <= 2 register rounds of up to five radix-2 stages (three for a fused two-transform tile, whose
+//     middle round runs 4+5 stages back to back in registers) separated by one block barrier each;
 //   * 128-bit stores of the finished rows straight from registers.
 // The kernel is bound by the integer multiply pipe (IMAD.HI on "fmaheavy"), not by HBM: see profiles/.
 #include "ntt_tile.cuh"
@@ -47,8 +48,7 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(const PassParams 
     const uint32_t zero = gf::opaque_zero();
     const uint32_t groups = (P.nstrips + P.strips_per_item - 1) / P.strips_per_item;
     const uint32_t nitems = P.nsets * groups;
-    const uint32_t nrounds = num_rounds(P.log_r);
-    const uint32_t total_rounds = nrounds * P.nxf;
+    const uint32_t nsteps = num_steps(P.log_r, P.nxf);
 
     TileIter cur; cur.item = blockIdx.x;
     if (!iter_decode(P, groups, nitems, cur)) return;
@@ -61,28 +61,30 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(const PassParams 
         cp_async_wait_all();
         __syncthreads();                                  // tile + tables of `cur` have landed
         const bool active = thread_active(P, tid, cur.strip);
+        const uint4* tw0 = tabs + (tb * P.nxf) * R;
+        const uint4* tw1 = tw0 + R;
         RoundRegs r;
         TileIter nxt = cur;
         bool has_next = false;
-        for (uint32_t rr = 0; rr < total_rounds; ++rr) {
-            const uint32_t xfi = rr >= nrounds ? 1u : 0u, k = rr - xfi * nrounds;
-            const bool last = rr + 1 == total_rounds;
-            if (active) round_read(P, xfi, k, tid, tile, r);
+        for (uint32_t s = 0; s < nsteps; ++s) {
+            const Step st = step_of(P.log_r, P.nxf, s);
+            const bool last = s + 1 == nsteps;
+            if (active) round_read(P, st.k, st.xfi, tid, tile, r);
             if (last) {
                 __syncthreads();                          // every slot is in registers: the tile buffer is free
                 has_next = iter_next(P, groups, nitems, nxt);
-                if (has_next) {                           // prefetch under the last round's butterflies
+                if (has_next) {                           // prefetch under the last step's butterflies
                     load_tile(P, nxt.set, nxt.strip, tid, tile);
                     if (nxt.set != cur.set)
                         for (uint32_t x = 0; x < P.nxf; ++x) build_table(P, x, nxt.set, tid, tabs + ((tb ^ 1u) * P.nxf + x) * R);
                 }
             }
-            if (active) round_math(P, xfi, k, tid, cur.set, tabs + (tb * P.nxf + xfi) * R, r, zero);
+            if (active) round_math(P, st, tid, cur.set, tw0, tw1, r, zero);
             if (!last) {
-                if (active) round_write_tile(P, xfi, k, tid, tile, r);
+                if (active) round_write_tile(P, st.k, st.xfi, tid, tile, r);
                 __syncthreads();
             } else if (active) {
-                round_write_global(P, k, tid, cur.set, cur.strip, r);
+                round_write_global(P, st, tid, cur.set, cur.strip, r);
             }
         }
         if (!has_next) break;

@@ -6,20 +6,28 @@
 //     MFA twiddle loop    ntt.cpp:421-431   (here: folded into the butterfly twiddles of the next pass, see below)
 //     scaling loop        RS.cpp:51-59      (here: folded into butterfly twiddles + one uniform pre-scale)
 // It is written as plain `__host__ __device__` code over an abstract "thread id" so that exactly the same
-// index/twiddle logic can be executed thread-by-thread on the CPU (tests/emulate_tile.cpp) before it ever
+// index/twiddle logic can be executed thread-by-thread on the CPU (tests/emulate_tile.cu) before it ever
 // touches a GPU.
 //
-// Geometry.  A tile is R = 2^LR rows (blocks) x WT words, R*WT = 16384 words = 4096 16-byte chunks (64 KiB of
-// shared memory).  256 threads; thread (j, q) owns chunk column q (4 consecutive words of every row: the
-// word dimension is a pure batch dimension, SURVEY 7 "hard part 2") and, in every round, 16 rows.  With
-// Q = WT/4 chunks per row:  q = tid % Q,  j = tid / Q  in [0, R/16).
+// Geometry.  A tile is R = 2^LR rows (blocks) x WT words, R*WT = 16384 words (64 KiB of shared memory), stored as
+// 16-byte chunks: chunk (row p, q) at index p*(WT/4)+q.  256 threads; thread (j, q2) owns the word PAIR q2 of every
+// row it touches (the word dimension is a pure batch dimension, SURVEY 7 "hard part 2") and, in every round,
+// 32 rows: q2 = tid % (WT/2), j = tid / (WT/2) in [0, R/32).  Thirty-two rows x two words = 64 data registers.
 //
-// Rounds.  A size-R DIT transform runs ceil(LR/4) rounds; round k handles index bits [lb, lb+4), lb = min(4k, LR-4),
-// executing the radix-2 stages for bits >= 4k only.  In a round a thread holds the 16 slots
-//     r_i = ((j >> lb) << (lb+4)) | (i << lb) | (j & (2^lb - 1)),   i = 0..15
-// in registers (16 x uint4), performs up to 4 stages x 8 butterflies x 4 words, and writes the slots back in
-// place; one block barrier separates rounds.  Slot r of a DIT transform initially holds input element
-// bitrev_LR(r) and finally holds output element r.
+// Rounds.  A size-R DIT transform runs ceil(LR/5) <= 2 rounds.  Round 0 holds index bits [0,5) in-thread and
+// executes the stages of bits [0, min(5,LR)); round 1 holds bits [LR-5, LR) and executes the stages of bits
+// [5, LR).  In a round a thread holds the 32 slots
+//     r_i = ((j >> lb) << (lb+5)) | (i << lb) | (j & (2^lb - 1)),   i = 0..31
+// in registers, performs up to 5 stages x 16 butterflies x 2 words, and writes the slots back in place; one
+// block barrier separates rounds.  Slot r of a DIT transform initially holds input element bitrev_LR(r) and
+// finally holds output element r.
+//
+// Fused tiles (two transforms back to back, the "BC" pass of the encoder): the second transform wants its input
+// bit-reversed, i.e. its slot r' lives at tile row bitrev(r').  The 32 rows a thread holds in the LAST round of
+// the first transform (rows differing in the top five bits) are exactly the 32 slots of one thread of the FIRST
+// round of the second transform (slots differing in the low five bits), only renumbered i -> brev5(i).  So that
+// pair of rounds is executed back to back in registers: 18 stages of a 512-point fused tile cost 3 shared-memory
+// round trips instead of 4 (or 6 with radix-16 rounds).
 //
 // Twiddles.  All twiddles are powers of g = GF_Root(2^20) (GF(p).cpp:267-276).  A transform is described by two
 // exponents (mod 2^20):  zeta = g^z is the primitive R-th root used by this tile, theta = g^t an *input twist*:
@@ -39,35 +47,38 @@
 
 namespace fecc {
 
-constexpr int kThreads        = 256;
-constexpr int kTileChunks     = 4096;            // 16-byte chunks per tile
-constexpr int kTileBytes      = kTileChunks * 16;
-constexpr int kMaxLogR        = 10;
-constexpr int kMinLogR        = 4;
+constexpr int kThreads    = 256;
+constexpr int kTileChunks = 4096;            // 16-byte chunks per tile
+constexpr int kTileBytes  = kTileChunks * 16;
+constexpr int kMaxLogR    = 10;
+constexpr int kMinLogR    = 5;
+constexpr int kRows       = 32;              // rows held by a thread in a round
+constexpr int kStages     = 5;               // radix-2 stages per full round
 
-struct Xform { uint32_t z, t0, t1; };            // tile root g^z; input twist g^(t0 + set*t1)   (exponents mod 2^20)
+struct Xform { uint32_t z, t0, t1; };        // tile root g^z; input twist g^(t0 + set*t1)   (exponents mod 2^20)
 
 struct PassParams {
     const uint32_t* src;
     uint32_t*       dst;
-    const uint4*    tw;                          // g^e for e in [0, 2^20): {w, Whi, Wlo, 0}
-    uint32_t pitch4;                             // row pitch in 16-byte chunks
-    uint32_t s4;                                 // valid 16-byte chunks per row (ceil(SIZE/4))
-    uint32_t log_r;                              // log2(rows per tile)
-    uint32_t nsets;                              // number of independent row sets
-    uint32_t nstrips;                            // ceil(s4 / Q)
-    uint32_t strips_per_item;                    // consecutive strips of one set handled by one CTA visit
+    const uint4*    tw;                      // g^e for e in [0, 2^20): {w, Whi, Wlo, 0}
+    uint32_t pitch4;                         // row pitch in 16-byte chunks
+    uint32_t s4;                             // valid 16-byte chunks per row (ceil(SIZE/4))
+    uint32_t log_r;                          // log2(rows per tile), 5..10
+    uint32_t nsets;                          // number of independent row sets
+    uint32_t nstrips;                        // ceil(s4 / (WT/4))
+    uint32_t strips_per_item;                // consecutive strips of one set handled by one CTA visit
     uint32_t src_set_stride, src_row_stride, dst_set_stride, dst_row_stride;             // in rows
-    uint32_t nxf;                                // 1, or 2 = two transforms back to back on the same tile
+    uint32_t nxf;                            // 1, or 2 = two transforms back to back on the same tile
     Xform    xf[2];
-    uint32_t prescale;                           // multiply every input word by the constant below (1/N)
+    uint32_t prescale;                       // multiply every input word by the constant below (1/N)
     uint32_t pw, pwhi, pwlo;
-    uint32_t canonical_out;                      // reduce stored words to [0,P)
-    uint32_t parity;                             // Q==4 layout: swap the two rows of a pair when popcount(row>>1) is odd
+    uint32_t canonical_out;                  // reduce stored words to [0,P)
+    uint32_t parity;                         // 64-byte rows (LR == 10): swap the rows of a pair when popcount(row>>1) is odd
 };
 
 FECC_HD uint32_t bitrev(uint32_t x, uint32_t bits)
 {
+    if (bits == 0) return 0;
 #if defined(__CUDA_ARCH__)
     return __brev(x) >> (32 - bits);
 #else
@@ -83,23 +94,26 @@ FECC_HD uint32_t popc32(uint32_t x)
 #endif
 }
 
-// chunk index (in uint4 units) of (physical row p, chunk q) inside the tile
-FECC_HD uint32_t tile_chunk(uint32_t p, uint32_t q, uint32_t qlog, uint32_t parity)
-{
-    if (parity) p ^= popc32(p >> 1) & 1u;
-    return (p << qlog) | q;
-}
+// compile-time helpers for the unrolled slot loops
+FECC_HD constexpr uint32_t par5(int i)  { return ((i) ^ (i >> 1) ^ (i >> 2) ^ (i >> 3) ^ (i >> 4)) & 1u; }       // popcount(i) & 1
+FECC_HD constexpr int      brev5(int i) { return ((i & 1) << 4) | ((i & 2) << 2) | (i & 4) | ((i & 8) >> 2) | ((i & 16) >> 4); }
+FECC_HD constexpr int      brev4(int i) { return ((i & 1) << 3) | ((i & 2) << 1) | ((i & 4) >> 1) | ((i & 8) >> 3); }
+FECC_HD constexpr uint32_t par4(int i)  { return (0x6996u >> i) & 1u; }
 
-// Rounds of a size-2^LR transform: nr = ceil(LR/4).  Round 0 executes the first rem = LR - 4(nr-1) stages (bits
-// [0, rem)) with bits 0..3 in-thread; round k >= 1 executes the four stages of bits [lb, lb+4), lb = rem + 4(k-1).
-// Putting the short round first leaves a full four-stage round at the end of the tile, which is the compute that
-// hides the next tile's cp.async loads (ntt_pass.cu).
-FECC_HD uint32_t num_rounds(uint32_t LR) { return (LR + 3) >> 2; }
-FECC_HD void round_bits(uint32_t LR, uint32_t k, uint32_t& lb, uint32_t& blo, uint32_t& bhi)
+FECC_HD uint32_t num_rounds(uint32_t LR) { return LR > (uint32_t)kStages ? 2u : 1u; }
+
+// Steps of a tile.  nxf == 1: rounds 0..nr-1.  nxf == 2: rounds 0..nr-2 of transform 0, then the FUSED step
+// (last round of transform 0 + round 0 of transform 1 in registers), then rounds 1..nr-1 of transform 1.
+FECC_HD uint32_t num_steps(uint32_t LR, uint32_t nxf) { const uint32_t nr = num_rounds(LR); return nxf == 2 ? 2 * nr - 1 : nr; }
+struct Step { uint32_t xfi, k; bool fused; };
+FECC_HD Step step_of(uint32_t LR, uint32_t nxf, uint32_t s)
 {
-    const uint32_t rem = LR - 4 * (num_rounds(LR) - 1);
-    if (k == 0) { lb = 0; blo = 0; bhi = rem; }
-    else        { lb = rem + 4 * (k - 1); blo = lb; bhi = lb + 4; }
+    const uint32_t nr = num_rounds(LR);
+    Step st;
+    if (nxf == 1 || s + 1 < nr) { st.xfi = 0; st.k = s; st.fused = false; }
+    else if (s + 1 == nr)       { st.xfi = 0; st.k = s; st.fused = true; }
+    else                        { st.xfi = 1; st.k = s + 1 - nr; st.fused = false; }
+    return st;
 }
 
 // exponent of heap entry idx (1 <= idx < R) of the stage table
@@ -114,42 +128,57 @@ FECC_HD uint32_t table_exponent(uint32_t idx, uint32_t LR, uint32_t z, uint32_t 
     return ((z * n + t) << (LR - 1 - b)) & (gf::M - 1);
 }
 
-// One butterfly on 4 words:  (a, b) <- (a + w*b, a - w*b)
-FECC_HD void bfly4(uint4& a, uint4& b, const uint4& w, uint32_t zero)
+FECC_HD uint2 canon2(uint2 v) { v.x = gf::canon(v.x); v.y = gf::canon(v.y); return v; }
+
+// One butterfly on a word pair:  (a, b) <- (a + w*b, a - w*b)
+FECC_HD void bfly2(uint2& a, uint2& b, const uint4& w, uint32_t zero)
 {
     uint32_t v;
     v = gf::mul(b.x, w.x, w.y, w.z, zero); b.x = gf::subl(a.x, v); a.x = gf::addl(a.x, v);
     v = gf::mul(b.y, w.x, w.y, w.z, zero); b.y = gf::subl(a.y, v); a.y = gf::addl(a.y, v);
-    v = gf::mul(b.z, w.x, w.y, w.z, zero); b.z = gf::subl(a.z, v); a.z = gf::addl(a.z, v);
-    v = gf::mul(b.w, w.x, w.y, w.z, zero); b.w = gf::subl(a.w, v); a.w = gf::addl(a.w, v);
+}
+// the same with twiddle 1: b only has to be brought into [0,P) (two ALU instructions) for the lazy add/sub
+FECC_HD void bfly2_trivial(uint2& a, uint2& b)
+{
+    const uint2 t = canon2(b);
+    b.x = gf::subl(a.x, t.x); a.x = gf::addl(a.x, t.x);
+    b.y = gf::subl(a.y, t.y); a.y = gf::addl(a.y, t.y);
 }
 
-FECC_HD uint4 canon4(uint4 v) { v.x = gf::canon(v.x); v.y = gf::canon(v.y); v.z = gf::canon(v.z); v.w = gf::canon(v.w); return v; }
+struct ThreadPos { uint32_t q2, j, q2log; };
+FECC_HD ThreadPos thread_pos(uint32_t LR, uint32_t tid)
+{
+    ThreadPos t; t.q2log = 13 - LR; t.q2 = tid & ((1u << t.q2log) - 1u); t.j = tid >> t.q2log; return t;
+}
 
 // Slot bookkeeping of one thread in one round.
 struct RoundCtx {
-    uint32_t lb, blo, bhi;    // bits [lb, lb+4) are in-thread; the stages of bits [blo, bhi) are executed
+    uint32_t lb, blo, bhi;    // bits [lb, lb+5) are in-thread; the stages of bits [blo, bhi) are executed
     uint32_t jbase;           // slot index with the in-thread bits zero
     uint32_t jlow;            // low lb bits of j (= low lb bits of every slot of this thread)
 };
-
 FECC_HD RoundCtx make_round(uint32_t LR, uint32_t k, uint32_t j)
 {
     RoundCtx c;
-    round_bits(LR, k, c.lb, c.blo, c.bhi);
+    if (k == 0) { c.lb = 0; c.blo = 0; c.bhi = LR < (uint32_t)kStages ? LR : (uint32_t)kStages; }
+    else        { c.lb = LR - kStages; c.blo = kStages; c.bhi = LR; }
     c.jlow  = j & ((1u << c.lb) - 1u);
-    c.jbase = ((j >> c.lb) << (c.lb + 4)) | c.jlow;
+    c.jbase = ((j >> c.lb) << (c.lb + kStages)) | c.jlow;
     return c;
 }
 
-// The register-resident part of a round: up to four radix-2 DIT stages on the thread's 16 slots x 4 words.
-// tw points at the heap-ordered stage table of the current transform (shared memory on the device).
-FECC_HD void round_compute(uint4 (&x)[16], const RoundCtx& c, const uint4* tw, uint32_t zero)
+struct RoundRegs { uint2 x[kRows]; };
+
+// Up to five radix-2 DIT stages on the thread's 32 slots x 2 words.  tw points at the heap-ordered stage table of the
+// current transform (shared memory on the device).  BREV: the registers are numbered in the order of the PREVIOUS
+// transform's last round (fused tiles): this transform's slot i is register brev5(i).
+template <bool BREV>
+FECC_HD void round_compute(uint2 (&x)[kRows], const RoundCtx& c, const uint4* tw, uint32_t zero)
 {
     const uint32_t sb = 1u << c.lb;                     // table stride between consecutive in-thread twiddles
     const uint4* tb = tw + c.jlow;
 #pragma unroll
-    for (int beta = 0; beta < 4; ++beta) {
+    for (int beta = 0; beta < kStages; ++beta) {
         const uint32_t b = c.lb + beta;
         if (b >= c.blo && b < c.bhi) {
             const uint4* twp = tb + (sb << beta);       // heap entry 2^b + jlow (+ m * 2^lb)
@@ -157,10 +186,10 @@ FECC_HD void round_compute(uint4 (&x)[16], const RoundCtx& c, const uint4* tw, u
             for (int m = 0; m < (1 << beta); ++m) {
                 const uint4 w = *twp; twp += sb;
 #pragma unroll
-                for (int hi = 0; hi < (8 >> beta); ++hi) {
+                for (int hi = 0; hi < (16 >> beta); ++hi) {
                     const int i0 = (hi << (beta + 1)) | m;
                     const int i1 = i0 | (1 << beta);
-                    bfly4(x[i0], x[i1], w, zero);
+                    bfly2(x[BREV ? brev5(i0) : i0], x[BREV ? brev5(i1) : i1], w, zero);
                 }
             }
         }
@@ -168,32 +197,26 @@ FECC_HD void round_compute(uint4 (&x)[16], const RoundCtx& c, const uint4* tw, u
 }
 
 // Round 0 of a PLAIN transform (no input twist): the twiddle of every pair whose low bits are zero is 1, which is
-// known at compile time because lb = 0 makes the table index depend on the in-thread index only.  Those
-// butterflies need no product: the b operand is merely brought to [0,P) (two ALU instructions) so that the lazy
-// add/sub stay closed.  The uniform pre-scale by 1/N (RS.cpp:51,54) is folded into stage 0, whose 8 butterflies
-// then cost two products each instead of one product plus two pre-scale products.
-FECC_HD void round0_plain(uint4 (&x)[16], const RoundCtx& c, const uint4* tw, bool PRESCALE, uint32_t pw, uint32_t pwhi, uint32_t pwlo, uint32_t zero)
+// known at compile time because lb = 0 makes the table index depend on the in-thread index only (31 of the 80
+// butterflies of a full round).  The uniform pre-scale by 1/N (RS.cpp:51,54) is folded into stage 0, whose 16
+// butterflies then cost two products each instead of one product plus two pre-scale products.
+FECC_HD void round0_plain(uint2 (&x)[kRows], const RoundCtx& c, const uint4* tw, bool prescale, uint32_t pw, uint32_t pwhi, uint32_t pwlo, uint32_t zero)
 {
-    const uint4 cw = {pw, pwhi, pwlo, 0};
 #pragma unroll
-    for (int hi = 0; hi < 8; ++hi) {                       // stage 0: all twiddles are 1
-        uint4& a = x[2 * hi]; uint4& b = x[2 * hi + 1];
-        if (PRESCALE) {
-            a.x = gf::mul(a.x, cw.x, cw.y, cw.z, zero); a.y = gf::mul(a.y, cw.x, cw.y, cw.z, zero);
-            a.z = gf::mul(a.z, cw.x, cw.y, cw.z, zero); a.w = gf::mul(a.w, cw.x, cw.y, cw.z, zero);
-            b.x = gf::mul(b.x, cw.x, cw.y, cw.z, zero); b.y = gf::mul(b.y, cw.x, cw.y, cw.z, zero);
-            b.z = gf::mul(b.z, cw.x, cw.y, cw.z, zero); b.w = gf::mul(b.w, cw.x, cw.y, cw.z, zero);
+    for (int hi = 0; hi < 16; ++hi) {                       // stage 0: all twiddles are 1
+        uint2& a = x[2 * hi]; uint2& b = x[2 * hi + 1];
+        if (prescale) {
+            a.x = gf::mul(a.x, pw, pwhi, pwlo, zero); a.y = gf::mul(a.y, pw, pwhi, pwlo, zero);
+            b.x = gf::mul(b.x, pw, pwhi, pwlo, zero); b.y = gf::mul(b.y, pw, pwhi, pwlo, zero);
+            uint32_t t;
+            t = b.x; b.x = gf::subl(a.x, t); a.x = gf::addl(a.x, t);
+            t = b.y; b.y = gf::subl(a.y, t); a.y = gf::addl(a.y, t);
         } else {
-            b = canon4(b);
+            bfly2_trivial(a, b);
         }
-        uint32_t t;
-        t = b.x; b.x = gf::subl(a.x, t); a.x = gf::addl(a.x, t);
-        t = b.y; b.y = gf::subl(a.y, t); a.y = gf::addl(a.y, t);
-        t = b.z; b.z = gf::subl(a.z, t); a.z = gf::addl(a.z, t);
-        t = b.w; b.w = gf::subl(a.w, t); a.w = gf::addl(a.w, t);
     }
 #pragma unroll
-    for (int beta = 1; beta < 4; ++beta) {
+    for (int beta = 1; beta < kStages; ++beta) {
         if ((uint32_t)beta < c.bhi) {
             const uint4* twb = tw + (1u << beta);
 #pragma unroll
@@ -201,47 +224,21 @@ FECC_HD void round0_plain(uint4 (&x)[16], const RoundCtx& c, const uint4* tw, bo
                 uint4 w = {0, 0, 0, 0};
                 if (m) w = twb[m];
 #pragma unroll
-                for (int hi = 0; hi < (8 >> beta); ++hi) {
+                for (int hi = 0; hi < (16 >> beta); ++hi) {
                     const int i0 = (hi << (beta + 1)) | m;
                     const int i1 = i0 | (1 << beta);
-                    if (m) {
-                        bfly4(x[i0], x[i1], w, zero);
-                    } else {
-                        uint4& a = x[i0]; uint4 b = canon4(x[i1]);
-                        x[i1].x = gf::subl(a.x, b.x); a.x = gf::addl(a.x, b.x);
-                        x[i1].y = gf::subl(a.y, b.y); a.y = gf::addl(a.y, b.y);
-                        x[i1].z = gf::subl(a.z, b.z); a.z = gf::addl(a.z, b.z);
-                        x[i1].w = gf::subl(a.w, b.w); a.w = gf::addl(a.w, b.w);
-                    }
+                    if (m) bfly2(x[i0], x[i1], w, zero); else bfly2_trivial(x[i0], x[i1]);
                 }
             }
         }
     }
 }
 
-// Compile-time helpers for the unrolled slot loops
-FECC_HD constexpr uint32_t par4(int i)  { return (0x6996u >> i) & 1u; }                                   // popcount(i) & 1
-FECC_HD constexpr int      brev4(int i) { return ((i & 1) << 3) | ((i & 2) << 1) | ((i & 4) >> 1) | ((i & 8) >> 3); }
-
-FECC_HD void prescale16(uint4 (&x)[16], uint32_t w, uint32_t whi, uint32_t wlo, uint32_t zero)
+FECC_HD void prescale_all(uint2 (&x)[kRows], uint32_t w, uint32_t whi, uint32_t wlo, uint32_t zero)
 {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        x[i].x = gf::mul(x[i].x, w, whi, wlo, zero);
-        x[i].y = gf::mul(x[i].y, w, whi, wlo, zero);
-        x[i].z = gf::mul(x[i].z, w, whi, wlo, zero);
-        x[i].w = gf::mul(x[i].w, w, whi, wlo, zero);
-    }
+    for (int i = 0; i < kRows; ++i) { x[i].x = gf::mul(x[i].x, w, whi, wlo, zero); x[i].y = gf::mul(x[i].y, w, whi, wlo, zero); }
 }
-
-} // namespace fecc
-
-// ---------------------------------------------------------------------------------------------------------------
-// Per-thread steps of a tile.  The kernel (ntt_pass.cu) runs them with block barriers in between; the CPU
-// emulation (tests/emulate_tile.cu) runs each step for tid = 0..255 in turn, which is equivalent because within a
-// step a thread only touches its own slots.
-// ---------------------------------------------------------------------------------------------------------------
-namespace fecc {
 
 // P.xf[xfi] with a runtime xfi would make the compiler copy the kernel parameters to local memory
 FECC_HD Xform get_xf(const PassParams& P, uint32_t xfi)
@@ -253,11 +250,14 @@ FECC_HD Xform get_xf(const PassParams& P, uint32_t xfi)
     return x;
 }
 
-struct ThreadPos { uint32_t q, j, qlog, Q; };
-FECC_HD ThreadPos thread_pos(const PassParams& P, uint32_t tid)
-{
-    ThreadPos t; t.qlog = 12 - P.log_r; t.Q = 1u << t.qlog; t.q = tid & (t.Q - 1); t.j = tid >> t.qlog; return t;
-}
+} // namespace fecc
+
+// ---------------------------------------------------------------------------------------------------------------
+// Per-thread steps of a tile.  The kernel (ntt_pass.cu) runs them with block barriers in between; the CPU
+// emulation (tests/emulate_tile.cu) runs each step for tid = 0..255 in turn, which is equivalent because within a
+// step a thread only touches its own slots.
+// ---------------------------------------------------------------------------------------------------------------
+namespace fecc {
 
 FECC_HD void copy16(uint4* dst_smem, const uint4* src_gmem)
 {
@@ -274,10 +274,9 @@ FECC_HD void build_table(const PassParams& P, uint32_t xfi, uint32_t set, uint32
 {
     const uint32_t R = 1u << P.log_r;
     const Xform xf = get_xf(P, xfi);
-    const uint32_t z = xf.z;
     const uint32_t t = (xf.t0 + set * xf.t1) & (gf::M - 1);
     for (uint32_t idx = tid; idx < R; idx += kThreads)
-        if (idx) copy16(tw_s + idx, P.tw + table_exponent(idx, P.log_r, z, t));
+        if (idx) copy16(tw_s + idx, P.tw + table_exponent(idx, P.log_r, xf.z, t));
 }
 
 // Issue the (asynchronous) loads of tile (set, strip).  Thread tid moves the 16 chunks c = tid + 256*m: tile row
@@ -302,85 +301,96 @@ FECC_HD void load_tile(const PassParams& P, uint32_t set, uint32_t strip, uint32
     }
 }
 
-struct RoundRegs { uint4 x[16]; };
-
 FECC_HD bool thread_active(const PassParams& P, uint32_t tid, uint32_t strip)
 {
-    const ThreadPos tp = thread_pos(P, tid);
-    return strip * tp.Q + tp.q < P.s4;                          // partial last strip: column chunk beyond the row
+    const ThreadPos tp = thread_pos(P.log_r, tid);
+    const uint32_t words2 = strip * (8192u >> P.log_r) + tp.q2;     // word-pair column inside the row
+    return (words2 >> 1) < P.s4;                                    // partial last strip: beyond the row's last chunk
 }
 
-// Tile chunk of the thread's slot i in round c:  physical row = slot (first transform) or bitrev(slot) (second
-// transform of a fused tile), rows of a pair swapped by popcount parity when P.parity.  All variants reduce to
-// "base + i*step" (or base ^ const) so that a round spends one ALU instruction per 16-byte access.
+// Tile address (in uint2 units) of the thread's slot i in round c:  physical row = slot (first transform, and the
+// fused step) or bitrev(slot) (later rounds of the second transform); the rows of a pair are swapped by popcount
+// parity when P.parity.  All variants reduce to "base + i*step" (or base ^ const): one ALU instruction per access.
 #define FECC_SLOT_LOOP(ACCESS)                                                                                     \
     if (P.parity) {                    /* identity placement only: plan.h never combines parity with a fused tile */ \
         if (c.lb == 0) {                                                                                           \
-            const uint32_t B = ((tp.j << 6) | tp.q) ^ ((popc32(tp.j) & 1u) << 2);                                  \
-            _Pragma("unroll") for (int i = 0; i < 16; ++i) { const uint32_t a = B ^ (uint32_t)((i ^ (int)par4(i >> 1)) << 2); ACCESS(i, a); } \
+            const uint32_t B = ((tp.j << 8) | tp.q2) ^ ((popc32(tp.j) & 1u) << 3);                                 \
+            _Pragma("unroll") for (int i = 0; i < kRows; ++i) { const uint32_t a = B ^ (uint32_t)((i ^ (int)par5(i >> 1)) << 3); ACCESS(i, a); } \
         } else {                                                                                                   \
-            uint32_t a0 = ((c.jbase ^ (popc32(c.jbase >> 1) & 1u)) << 2) | tp.q;                                   \
-            const uint32_t step = 4u << c.lb;                                                                      \
-            _Pragma("unroll") for (int i = 0; i < 16; ++i) { const uint32_t a = a0 ^ (par4(i) << 2); ACCESS(i, a); a0 += step; } \
+            uint32_t a0 = ((c.jbase ^ (popc32(c.jbase >> 1) & 1u)) << 3) | tp.q2;                                  \
+            const uint32_t step = 8u << c.lb;                                                                      \
+            _Pragma("unroll") for (int i = 0; i < kRows; ++i) { const uint32_t a = a0 ^ (par5(i) << 3); ACCESS(i, a); a0 += step; } \
         }                                                                                                          \
-    } else if (xfi) {                                                                                              \
-        uint32_t a = (bitrev(c.jbase, LR) << tp.qlog) | tp.q;                                                      \
-        const uint32_t step = 1u << (LR - 4 - c.lb + tp.qlog);                                                     \
-        _Pragma("unroll") for (int k = 0; k < 16; ++k) { ACCESS(brev4(k), a); a += step; }                         \
+    } else if (brev) {                                                                                             \
+        uint32_t a = (bitrev(c.jbase, LR) << tp.q2log) | tp.q2;                                                    \
+        const uint32_t step = 1u << (LR - kStages - c.lb + tp.q2log);                                              \
+        _Pragma("unroll") for (int k = 0; k < kRows; ++k) { ACCESS(brev5(k), a); a += step; }                      \
     } else {                                                                                                       \
-        uint32_t a = (c.jbase << tp.qlog) | tp.q;                                                                  \
-        const uint32_t step = 1u << (c.lb + tp.qlog);                                                              \
-        _Pragma("unroll") for (int i = 0; i < 16; ++i) { ACCESS(i, a); a += step; }                                \
+        uint32_t a = (c.jbase << tp.q2log) | tp.q2;                                                                \
+        const uint32_t step = 1u << (c.lb + tp.q2log);                                                             \
+        _Pragma("unroll") for (int i = 0; i < kRows; ++i) { ACCESS(i, a); a += step; }                             \
     }
 
-// (a) read the thread's 16 slots of round k of transform xfi
-FECC_HD void round_read(const PassParams& P, uint32_t xfi, uint32_t k, uint32_t tid, const uint4* tile, RoundRegs& r)
+// (a) read the thread's 32 slots of a step.  brev = bit-reversed placement (rounds >= 1 of the second transform).
+FECC_HD void round_read(const PassParams& P, uint32_t k, uint32_t brev, uint32_t tid, const uint4* tile, RoundRegs& r)
 {
     const uint32_t LR = P.log_r;
-    const ThreadPos tp = thread_pos(P, tid);
+    const ThreadPos tp = thread_pos(LR, tid);
     const RoundCtx c = make_round(LR, k, tp.j);
-#define FECC_RD(I, A) r.x[I] = tile[A]
+    const uint2* t2 = reinterpret_cast<const uint2*>(tile);
+#define FECC_RD(I, A) r.x[I] = t2[A]
     FECC_SLOT_LOOP(FECC_RD)
 #undef FECC_RD
 }
 
-// (b) the butterflies
-FECC_HD void round_math(const PassParams& P, uint32_t xfi, uint32_t k, uint32_t tid, uint32_t set, const uint4* tw_s, RoundRegs& r, uint32_t zero)
+// (b) the butterflies of a step
+FECC_HD void round_math(const PassParams& P, const Step st, uint32_t tid, uint32_t set, const uint4* tw0, const uint4* tw1, RoundRegs& r, uint32_t zero)
 {
-    const ThreadPos tp = thread_pos(P, tid);
-    const RoundCtx c = make_round(P.log_r, k, tp.j);
-    const bool first = (xfi == 0 && k == 0);
-    const Xform xf = get_xf(P, xfi);
+    const uint32_t LR = P.log_r;
+    const ThreadPos tp = thread_pos(LR, tid);
+    const RoundCtx c = make_round(LR, st.k, tp.j);
+    const bool first = (st.xfi == 0 && st.k == 0);
+    const Xform xf = get_xf(P, st.xfi);
     const bool plain = ((xf.t0 + set * xf.t1) & (gf::M - 1)) == 0;
-    if (k == 0 && plain) {
-        round0_plain(r.x, c, tw_s, first && P.prescale, P.pw, P.pwhi, P.pwlo, zero);
+    const uint4* tw = st.xfi ? tw1 : tw0;
+    if (st.k == 0 && plain) {
+        round0_plain(r.x, c, tw, first && P.prescale, P.pw, P.pwhi, P.pwlo, zero);
     } else {
-        if (first && P.prescale) prescale16(r.x, P.pw, P.pwhi, P.pwlo, zero);
-        round_compute(r.x, c, tw_s, zero);
+        if (first && P.prescale) prescale_all(r.x, P.pw, P.pwhi, P.pwlo, zero);
+        round_compute<false>(r.x, c, tw, zero);
+    }
+    if (st.fused) {                                     // round 0 of the second transform on the same registers
+        const RoundCtx c1 = make_round(LR, 0, 0);       // lb = 0: no dependence on the thread's position
+        round_compute<true>(r.x, c1, tw1, zero);
     }
 }
 
-// (c) write back in place, or (last round of the last transform) store output element r to its global row
-FECC_HD void round_write_tile(const PassParams& P, uint32_t xfi, uint32_t k, uint32_t tid, uint4* tile, const RoundRegs& r)
+// (c) write back in place ...
+FECC_HD void round_write_tile(const PassParams& P, uint32_t k, uint32_t brev, uint32_t tid, uint4* tile, const RoundRegs& r)
 {
     const uint32_t LR = P.log_r;
-    const ThreadPos tp = thread_pos(P, tid);
+    const ThreadPos tp = thread_pos(LR, tid);
     const RoundCtx c = make_round(LR, k, tp.j);
-#define FECC_WR(I, A) tile[A] = r.x[I]
+    uint2* t2 = reinterpret_cast<uint2*>(tile);
+#define FECC_WR(I, A) t2[A] = r.x[I]
     FECC_SLOT_LOOP(FECC_WR)
 #undef FECC_WR
 }
-FECC_HD void round_write_global(const PassParams& P, uint32_t k, uint32_t tid, uint32_t set, uint32_t strip, const RoundRegs& r)
+
+// ... or (last step) store output element r to its global row.  After a fused step that is also the last step
+// (LR <= 5) register brev5(i) holds output element i of the second transform.
+FECC_HD void round_write_global(const PassParams& P, const Step st, uint32_t tid, uint32_t set, uint32_t strip, const RoundRegs& r)
 {
-    const ThreadPos tp = thread_pos(P, tid);
-    const RoundCtx c = make_round(P.log_r, k, tp.j);
-    const uint32_t gcol = strip * tp.Q + tp.q;
+    const ThreadPos tp = thread_pos(P.log_r, tid);
+    const RoundCtx c = st.fused ? make_round(P.log_r, 0, 0) : make_round(P.log_r, st.k, tp.j);
+    const uint32_t gcol2 = strip * (8192u >> P.log_r) + tp.q2;
     const uint32_t row0 = set * P.dst_set_stride + c.jbase * P.dst_row_stride;
-    uint4* g = reinterpret_cast<uint4*>(P.dst) + ((size_t)row0 * P.pitch4 + gcol);
-    const size_t gstep = ((size_t)P.dst_row_stride * P.pitch4) << c.lb;
+    uint2* g = reinterpret_cast<uint2*>(P.dst) + ((size_t)row0 * P.pitch4 * 2 + gcol2);
+    const size_t gstep = ((size_t)P.dst_row_stride * P.pitch4 * 2) << c.lb;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        *g = P.canonical_out ? canon4(r.x[i]) : r.x[i];
+    for (int i = 0; i < kRows; ++i) {
+        const uint2 v = st.fused ? r.x[brev5(i)] : r.x[i];
+        *g = P.canonical_out ? canon2(v) : v;
         g += gstep;
     }
 }

@@ -18,7 +18,7 @@
 //         forward DIT over k2 with input twist (rho^N1)^k2          (rho = root_2N, RS.cpp:51)
 //     D   for each j2, forward DIT over k1 (rows k1*N2+j2) with input twist (w^j2 * rho)^k1 -> parity row j1*N2+j2
 //   so the four-step twiddles (ntt.cpp:421-431) and the scaling rho^m (RS.cpp:54-58) never cost a multiplication.
-//   N <= 1024: a single pass (NTT) or a single fused pass (encode).   N < 16: see small_dft.cu.
+//   N <= 1024: a single pass (NTT) or a single fused pass (encode).   N < 32: see small_dft.cu.
 #pragma once
 #include <vector>
 #include <stdint.h>
@@ -39,7 +39,7 @@ inline PassParams base_pass(const Buffers& b, uint32_t log_r)
     p.pitch4 = b.pitch_words / 4;
     p.s4 = (b.size_words + 3) / 4;
     p.log_r = log_r;
-    const uint32_t Q = 4096u >> log_r;
+    const uint32_t Q = 4096u >> log_r;                                  // 16-byte chunks per tile row
     p.nstrips = (p.s4 + Q - 1) / Q;
     p.strips_per_item = p.nstrips >= 16 ? 4 : 1;
     p.nxf = 1;

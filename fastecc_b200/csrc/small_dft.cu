@@ -1,6 +1,6 @@
-// Degenerate orders N = 1, 2, 4, 8 (below the 16-row register block of ntt_pass_kernel) and the two layout
+// Degenerate orders N = 1, 2, 4, 8, 16 (below the 32-row register block of ntt_pass_kernel) and the two layout
 // helpers.  One thread per 16-byte column chunk evaluates the transform by its definition (Slow_NTT,
-// ntt.cpp:451-483) -- at most 8x8 products per word -- using the same power table and GF primitives as the main kernel.
+// ntt.cpp:451-483) -- at most 16x16 products per word -- using the same power table and GF primitives as the main kernel.
 #include "small_dft.h"
 #include "gf.cuh"
 
@@ -19,7 +19,7 @@ __device__ __forceinline__ uint4 add4(uint4 a, uint4 v)
 }
 __device__ __forceinline__ uint4 canon4s(uint4 v) { v.x = gf::canon(v.x); v.y = gf::canon(v.y); v.z = gf::canon(v.z); v.w = gf::canon(v.w); return v; }
 
-// out[k] = sum_n in[n] * g^(z*n*k)          (n, k < N <= 8)
+// out[k] = sum_n in[n] * g^(z*n*k)          (n, k < N <= 16)
 __device__ __forceinline__ void dft_small(const uint4* in, uint4* out, uint32_t N, uint32_t z, const uint4* tw, uint32_t zero)
 {
     for (uint32_t k = 0; k < N; ++k) {
@@ -37,7 +37,7 @@ __global__ void small_dft_kernel(uint32_t* data, uint32_t pitch4, uint32_t s4, u
     if (col >= s4) return;
     const uint32_t zero = gf::opaque_zero();
     uint4* d4 = reinterpret_cast<uint4*>(data);
-    uint4 x[8], y[8];
+    uint4 x[16], y[16];
     for (uint32_t n = 0; n < N; ++n) x[n] = d4[(size_t)n * pitch4 + col];
     if (!encode) {
         dft_small(x, y, N, z, tw, zero);
