@@ -38,8 +38,13 @@ __device__ __forceinline__ bool iter_next(const PassParams& P, uint32_t groups, 
     return iter_decode(P, groups, nitems, it);
 }
 
-__global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(const PassParams P)
+// LR / NXF / PARITY are compile-time: the kernel patches them into its copy of the parameters, so every shift,
+// stride and placement branch in ntt_tile.cuh folds to an immediate (keeps the 64 data registers from spilling).
+template <int LR, int NXF, int PARITY>
+__global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(const PassParams Pin)
 {
+    PassParams P = Pin;
+    P.log_r = LR; P.nxf = NXF; P.parity = PARITY;
     extern __shared__ __align__(128) uint4 smem[];
     uint4* tile = smem;                                   // 4096 chunks
     uint4* tabs = smem + kTileChunks;                     // [2 buffers][nxf][R]
@@ -98,21 +103,35 @@ size_t pass_smem_bytes(const PassParams& P)
     return (size_t)kTileBytes + (size_t)2 * P.nxf * ((size_t)16 << P.log_r);
 }
 
-cudaError_t launch_pass(const PassParams& P, int num_sms, cudaStream_t stream)
+template <int LR, int NXF, int PARITY>
+static cudaError_t launch_inst(const PassParams& P, unsigned grid, cudaStream_t stream)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileBytes + 4 * (16 << kMaxLogR));
+        cudaError_t e = cudaFuncSetAttribute(ntt_pass_kernel<LR, NXF, PARITY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kTileBytes + 2 * NXF * (16 << LR));
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
+    ntt_pass_kernel<LR, NXF, PARITY><<<grid, kThreads, pass_smem_bytes(P), stream>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pass(const PassParams& P, int num_sms, cudaStream_t stream)
+{
     const uint32_t groups = (P.nstrips + P.strips_per_item - 1) / P.strips_per_item;
     const unsigned long long nitems = (unsigned long long)P.nsets * groups;
     unsigned long long grid = (unsigned long long)num_sms * 2;
     if (grid > nitems) grid = nitems;
     if (grid == 0) return cudaSuccess;
-    ntt_pass_kernel<<<(unsigned)grid, kThreads, pass_smem_bytes(P), stream>>>(P);
-    return cudaGetLastError();
+    const unsigned g = (unsigned)grid;
+    if (P.parity != ((P.log_r == 10 && P.nxf == 1) ? 1u : 0u)) return cudaErrorInvalidValue;
+#define FECC_CASE(L) case L: return P.nxf == 2 ? launch_inst<L, 2, 0>(P, g, stream) : launch_inst<L, 1, (L == 10)>(P, g, stream);
+    switch (P.log_r) {
+        FECC_CASE(5) FECC_CASE(6) FECC_CASE(7) FECC_CASE(8) FECC_CASE(9) FECC_CASE(10)
+        default: return cudaErrorInvalidValue;
+    }
+#undef FECC_CASE
 }
 
 } // namespace fecc
