@@ -294,10 +294,19 @@ FECC_HD void load_tile(const PassParams& P, uint32_t set, uint32_t strip, uint32
     uint32_t cbase = (p0 << qlog) | qq;
     if (P.parity) cbase ^= (popc32(p0 >> 1) & 1u) << qlog;
     const uint32_t pbit = P.parity ? (1u << qlog) : 0u;
+    // four rotating source pointers: an LDGSTS keeps its address registers busy until the LSU has taken it, so
+    // reusing one pointer for consecutive copies serialises them on the long scoreboard
+    const uint4* gp[4] = {g, g + gstep, g + 2 * gstep, g + 3 * gstep};
+    const size_t gstep4 = 4 * gstep;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {                          // k = brev4(m): k-th consecutive source row
-        copy16(tile + ((cbase + 256u * (uint32_t)brev4(k)) ^ (par4(k) ? pbit : 0u)), g);
-        g += gstep;
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {                       // k = brev4(m): k-th consecutive source row
+            const int k = 4 * kk + u;
+            copy16(tile + ((cbase + 256u * (uint32_t)brev4(k)) ^ (par4(k) ? pbit : 0u)), gp[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) gp[u] += gstep4;
     }
 }
 

@@ -8,9 +8,10 @@
 #include "../fastecc_b200/csrc/ntt_tile.cuh"
 using namespace fecc;
 
-template <int MODE>
-__global__ void __launch_bounds__(256, 2) rb(PassParams P, int iters, uint32_t k, uint32_t* sink)
+template <int MODE, int LRT>
+__global__ void __launch_bounds__(256, 2) rb(PassParams Pin, int iters, uint32_t k, uint32_t* sink)
 {
+    PassParams P = Pin; P.log_r = LRT; P.nxf = 1; P.parity = (LRT == 10);
     extern __shared__ __align__(128) uint4 smem[];
     uint4* tile = smem; uint4* tw = smem + kTileChunks;
     const uint32_t tid = threadIdx.x, zero = gf::opaque_zero();
@@ -18,16 +19,17 @@ __global__ void __launch_bounds__(256, 2) rb(PassParams P, int iters, uint32_t k
     for (uint32_t i = tid; i < (1u << P.log_r); i += 256) tw[i] = P.tw[(i * 977u) & (gf::M - 1)];
     __syncthreads();
     RoundRegs r;
-    round_read(P, 0, k, tid, tile, r);
+    Step st; st.xfi = 0; st.k = k; st.fused = false;
+    round_read(P, k, 0, tid, tile, r);
     for (int it = 0; it < iters; ++it) {
-        if (MODE >= 1) round_read(P, 0, k, tid, tile, r);
-        round_math(P, 0, k, tid, 1 /*set (non-plain via t1)*/, tw, r, zero);
-        if (MODE >= 1) round_write_tile(P, 0, k, tid, tile, r);
+        if (MODE >= 1) round_read(P, k, 0, tid, tile, r);
+        round_math(P, st, tid, 1 /*set (non-plain via t1)*/, tw, tw, r, zero);
+        if (MODE >= 1) round_write_tile(P, k, 0, tid, tile, r);
         if (MODE >= 2) __syncthreads();
     }
     uint32_t acc = 0;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc ^= r.x[i].x ^ r.x[i].y ^ r.x[i].z ^ r.x[i].w;
+    for (int i = 0; i < kRows; ++i) acc ^= r.x[i].x ^ r.x[i].y;
     sink[blockIdx.x * 256 + tid] = acc;
 }
 
@@ -40,25 +42,34 @@ int main()
     uint32_t* sink; cudaMalloc(&sink, sms * 2 * 256 * 4);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     const int smem = kTileBytes + (16 << 10) ;
-    cudaFuncSetAttribute(rb<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(rb<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(rb<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(rb<0,10>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(rb<1,10>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(rb<2,10>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(rb<0,9>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(rb<1,9>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(rb<2,9>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     for (uint32_t LR : {10u, 9u}) {
         PassParams P{}; P.tw = tw; P.log_r = LR; P.nxf = 1; P.parity = (LR == 10); P.xf[0] = Xform{12345, 0, 777};
         P.s4 = 256; P.pitch4 = 256; P.nstrips = 1;
-        for (uint32_t k : {1u, 2u}) for (int ctas : {1, 2}) {
+        for (uint32_t k : {0u, 1u}) for (int ctas : {1, 2}) {
             const int iters = 200, grid = sms * ctas;
             auto run = [&](int mode) {
                 float best = 1e9;
                 for (int rep = 0; rep < 3; rep++) {
                     cudaEventRecord(e0);
-                    if (mode == 0) rb<0><<<grid, 256, smem>>>(P, iters, k, sink);
-                    if (mode == 1) rb<1><<<grid, 256, smem>>>(P, iters, k, sink);
-                    if (mode == 2) rb<2><<<grid, 256, smem>>>(P, iters, k, sink);
+                    if (LR == 10) {
+                    if (mode == 0) rb<0,10><<<grid, 256, smem>>>(P, iters, k, sink);
+                    if (mode == 1) rb<1,10><<<grid, 256, smem>>>(P, iters, k, sink);
+                    if (mode == 2) rb<2,10><<<grid, 256, smem>>>(P, iters, k, sink);
+                    } else {
+                    if (mode == 0) rb<0,9><<<grid, 256, smem>>>(P, iters, k, sink);
+                    if (mode == 1) rb<1,9><<<grid, 256, smem>>>(P, iters, k, sink);
+                    if (mode == 2) rb<2,9><<<grid, 256, smem>>>(P, iters, k, sink);
+                    }
                     cudaEventRecord(e1); cudaEventSynchronize(e1);
                     float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
                 }
-                const double warp_bfly_per_smsp = (double)iters * 128 /*bfly per thread per 4-stage round*/ * 8 * ctas / 4;
+                const double warp_bfly_per_smsp = (double)iters * ((k == 0 || LR == 10) ? 160 : 128) /*bfly per thread per round*/ * 8 * ctas / 4;
                 printf("LR=%u round k=%u ctas/SM=%d mode=%d: %.3f ms  -> %.2f cycles per warp-butterfly per SMSP (@1.965GHz)  [%s]\n", LR, k, ctas, mode, best,
                        best * 1e-3 * 1.965e9 / warp_bfly_per_smsp, cudaGetErrorString(cudaGetLastError()));
             };
