@@ -10,6 +10,7 @@
 #include <mutex>
 #include <vector>
 #include <atomic>
+#include <map>
 
 using namespace fecc;
 
@@ -34,6 +35,7 @@ struct Context {
     DevBuf scratch;      // Y buffer of the two-pass NTT
     DevBuf packed;       // repacked copy for unaligned device layouts
     DevBuf staging;      // device copy for the host (T**) entry points
+    std::map<uint32_t, std::vector<DevBuf>> tables;   // per (mode, log2 N): one table block per pass (plan.h table_bytes)
     cudaStream_t stream = nullptr;
 };
 
@@ -77,7 +79,19 @@ int run_aligned(Context* c, uint32_t* x, size_t N, size_t size, size_t pitch, in
         b.y = (uint32_t*)c->scratch.p;
     }
     std::vector<PassParams> plan = (mode == 2) ? plan_encode(b, N) : plan_ntt(b, N, mode == 1);
-    for (const PassParams& p : plan) { CUDA_TRY(launch_pass(p, c->num_sms, st)); g_launches++; }
+    std::vector<DevBuf>& tabs = c->tables[(uint32_t)mode << 8 | ilog2(N)];
+    if (tabs.empty()) {                                   // first use of this (mode, N): build the per-set stage tables
+        tabs.resize(plan.size());
+        for (size_t i = 0; i < plan.size(); ++i) {
+            CUDA_TRY(tabs[i].reserve(table_bytes(plan[i])));
+            CUDA_TRY(launch_build_tables(plan[i], (uint4*)tabs[i].p, st)); g_launches++;
+        }
+    }
+    for (size_t i = 0; i < plan.size(); ++i) {
+        plan[i].tables = (const uint4*)tabs[i].p;
+        plan[i].table_set_stride = table_sets(plan[i]) > 1 ? (plan[i].nxf << plan[i].log_r) : 0u;
+        CUDA_TRY(launch_pass(plan[i], c->num_sms, st)); g_launches++;
+    }
     return 0;
 }
 
@@ -166,6 +180,7 @@ void fastecc_b200_shutdown(void)
     cudaSetDevice(g_ctx->device);
     cudaDeviceSynchronize();
     g_ctx->scratch.release(); g_ctx->packed.release(); g_ctx->staging.release();
+    for (auto& kv : g_ctx->tables) for (auto& b : kv.second) b.release();
     if (g_ctx->d_tw) cudaFree(g_ctx->d_tw);
     if (g_ctx->stream) cudaStreamDestroy(g_ctx->stream);
     delete g_ctx; g_ctx = nullptr;

@@ -4,20 +4,55 @@
 //
 // Execution model: persistent CTAs of 256 threads, two per SM, each walking a sequence of
 // 64 KiB tiles (row set x column strip).  Per tile:
-//   * the tile and, when the row set changes, its twiddle table arrive by 16-byte cp.async (LDGSTS) straight into
-//     the bank-conflict-free shared-memory layout -- issued one tile AHEAD, right after the previous tile's last
-//     round has pulled its slots into registers, so the loads fly under a full four-stage round of butterflies;
+//   * one elected thread issues the TMA traffic: cp.async.bulk.tensor (3-D tensor map over [word][row-in-set][set],
+//     boxes of <= 256 rows) for the tile and, when the row set changes, one cp.async.bulk for the set's precomputed
+//     twiddle tables; completion is tracked by an mbarrier (expect_tx / complete_tx).  The next tile is requested
+//     right after the current tile's last step has pulled its slots into registers, so it flies under a full
+//     five-stage round of butterflies; out-of-range columns are zero-filled by the TMA unit;
 //   * ceil(LR/5) <= 2 register rounds of up to five radix-2 stages (three for a fused two-transform tile, whose
 //     middle round runs 4+5 stages back to back in registers) separated by one block barrier each;
-//   * 128-bit stores of the finished rows straight from registers.
+//   * 64-bit stores of the finished rows straight from registers.
 // The kernel is bound by the integer multiply pipe (IMAD.HI on "fmaheavy"), not by HBM: see profiles/.
 #include "ntt_tile.cuh"
 #include "ntt_pass.h"
+#include "plan.h"
+#include <cstring>
+#include <cstdlib>
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 namespace fecc {
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, uint32_t c0, uint32_t c1, uint32_t c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 struct TileIter {                       // the CTA's walk over (item -> strips)
     uint32_t item, set, strip, strip_end;
@@ -38,55 +73,79 @@ __device__ __forceinline__ bool iter_next(const PassParams& P, uint32_t groups, 
     return iter_decode(P, groups, nitems, it);
 }
 
-// LR / NXF / PARITY are compile-time: the kernel patches them into its copy of the parameters, so every shift,
-// stride and placement branch in ntt_tile.cuh folds to an immediate (keeps the 64 data registers from spilling).
-template <int LR, int NXF, int PARITY>
-__global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(const PassParams Pin)
+// LR / NXF / TMA are compile-time: the kernel patches them into its copy of the parameters, so every shift, stride
+// and placement branch in ntt_tile.cuh folds to an immediate (keeps the 64 data registers from spilling).
+template <int LR, int NXF, int TMA>
+__global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(const PassParams Pin, const __grid_constant__ CUtensorMap tmap)
 {
     PassParams P = Pin;
-    P.log_r = LR; P.nxf = NXF; P.parity = PARITY;
-    extern __shared__ __align__(128) uint4 smem[];
-    uint4* tile = smem;                                   // 4096 chunks
-    uint4* tabs = smem + kTileChunks;                     // [2 buffers][nxf][R]
-    const uint32_t R = 1u << P.log_r;
+    P.log_r = LR; P.nxf = NXF; P.use_tma = TMA;
+    extern __shared__ __align__(1024) uint4 smem[];
+    constexpr uint32_t R = 1u << LR;
+    uint4* tile = smem;                                   // 4096 chunks, natural row order
+    uint4* tabs = smem + kTileChunks;                     // [2 buffers][NXF][R]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tabs + 2 * NXF * R);
     const uint32_t tid  = threadIdx.x;
     const uint32_t zero = gf::opaque_zero();
     const uint32_t groups = (P.nstrips + P.strips_per_item - 1) / P.strips_per_item;
     const uint32_t nitems = P.nsets * groups;
-    const uint32_t nsteps = num_steps(P.log_r, P.nxf);
+    constexpr uint32_t nsteps = NXF == 2 ? (LR > kStages ? 3u : 1u) : (LR > kStages ? 2u : 1u);
+    constexpr uint32_t kWt = 16384u >> LR;                // words per tile row
+    constexpr uint32_t kRowsBox = R < 256u ? R : 256u;    // TMA box: kRowsBox rows x kWt words
+    constexpr uint32_t kBoxes = R / kRowsBox;
+    constexpr uint32_t kTableBytes = NXF * R * 16u;
 
     TileIter cur; cur.item = blockIdx.x;
     if (!iter_decode(P, groups, nitems, cur)) return;
     uint32_t tb = 0;                                      // table buffer used by the current tile
+    uint32_t phase = 0;
 
-    load_tile(P, cur.set, cur.strip, tid, tile);          // prologue: first tile + its tables
-    for (uint32_t x = 0; x < P.nxf; ++x) build_table(P, x, cur.set, tid, tabs + (tb * P.nxf + x) * R);
+    // request tile (set, strip) [+ the set's tables into buffer tbuf]
+    auto request = [&](uint32_t set, uint32_t strip, bool with_tables, uint32_t tbuf) {
+        if (TMA) {
+            if (tid == 0) {
+                fence_proxy_async();                      // order our earlier generic-proxy accesses to the tile before the async-proxy writes
+                mbar_expect_tx(bar, kTileBytes + (with_tables ? kTableBytes : 0u));
+#pragma unroll
+                for (uint32_t b = 0; b < kBoxes; ++b)
+                    tma_load_3d(tile + b * (kRowsBox * (kWt / 4)), &tmap, bar, strip * kWt, b * kRowsBox, set);
+                if (with_tables)
+                    bulk_load(tabs + tbuf * NXF * R, P.tables + (size_t)set * P.table_set_stride, kTableBytes, bar);
+            }
+        } else {
+            load_tile_cpasync(P, set, strip, tid, tile);
+            if (with_tables) load_tables_cpasync(P, set, tid, tabs + tbuf * NXF * R);
+        }
+    };
+
+    if (TMA) {
+        if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+        __syncthreads();
+    }
+    request(cur.set, cur.strip, true, tb);                // prologue: first tile + its tables
 
     for (;;) {
-        cp_async_wait_all();
-        __syncthreads();                                  // tile + tables of `cur` have landed
+        if (TMA) { mbar_wait(bar, phase); phase ^= 1u; }
+        else     { cp_async_wait_all(); __syncthreads(); }
         const bool active = thread_active(P, tid, cur.strip);
-        const uint4* tw0 = tabs + (tb * P.nxf) * R;
+        const uint4* tw0 = tabs + (tb * NXF) * R;
         const uint4* tw1 = tw0 + R;
         RoundRegs r;
         TileIter nxt = cur;
         bool has_next = false;
+#pragma unroll 1
         for (uint32_t s = 0; s < nsteps; ++s) {
-            const Step st = step_of(P.log_r, P.nxf, s);
+            const Step st = step_of(LR, NXF, s);
             const bool last = s + 1 == nsteps;
-            if (active) round_read(P, st.k, st.xfi, tid, tile, r);
+            if (active) round_read(P, st.k, st.xfi == 0, tid, tile, r);
             if (last) {
                 __syncthreads();                          // every slot is in registers: the tile buffer is free
                 has_next = iter_next(P, groups, nitems, nxt);
-                if (has_next) {                           // prefetch under the last step's butterflies
-                    load_tile(P, nxt.set, nxt.strip, tid, tile);
-                    if (nxt.set != cur.set)
-                        for (uint32_t x = 0; x < P.nxf; ++x) build_table(P, x, nxt.set, tid, tabs + ((tb ^ 1u) * P.nxf + x) * R);
-                }
+                if (has_next) request(nxt.set, nxt.strip, nxt.set != cur.set, tb ^ 1u);   // flies under the last step's butterflies
             }
             if (active) round_math(P, st, tid, cur.set, tw0, tw1, r, zero);
             if (!last) {
-                if (active) round_write_tile(P, st.k, st.xfi, tid, tile, r);
+                if (active) round_write_tile(P, st.k, st.xfi == 0, tid, tile, r);
                 __syncthreads();
             } else if (active) {
                 round_write_global(P, st, tid, cur.set, cur.strip, r);
@@ -98,35 +157,96 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(const PassParams 
     }
 }
 
-size_t pass_smem_bytes(const PassParams& P)
+// One thread per table entry: tables[set][xfi][idx] = g^exponent (entry 0 of every table is unused).
+__global__ void build_tables_kernel(const PassParams P, uint4* out, uint32_t nsets_tab)
 {
-    return (size_t)kTileBytes + (size_t)2 * P.nxf * ((size_t)16 << P.log_r);
+    const uint32_t R = 1u << P.log_r;
+    const size_t total = (size_t)nsets_tab * P.nxf * R;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t idx = (uint32_t)(i & (R - 1));
+        const uint32_t xfi = (uint32_t)((i >> P.log_r) % P.nxf);
+        const uint32_t set = (uint32_t)((i >> P.log_r) / P.nxf);
+        out[i] = idx ? P.tw[table_entry_exponent(P, xfi, set, idx)] : make_uint4(0, 0, 0, 0);
+    }
 }
 
-template <int LR, int NXF, int PARITY>
-static cudaError_t launch_inst(const PassParams& P, unsigned grid, cudaStream_t stream)
+cudaError_t launch_build_tables(PassParams& P, uint4* out, cudaStream_t stream)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(ntt_pass_kernel<LR, NXF, PARITY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             kTileBytes + 2 * NXF * (16 << LR));
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    ntt_pass_kernel<LR, NXF, PARITY><<<grid, kThreads, pass_smem_bytes(P), stream>>>(P);
+    const uint32_t ns = table_sets(P);
+    P.tables = out;
+    P.table_set_stride = ns > 1 ? (P.nxf << P.log_r) : 0u;
+    build_tables_kernel<<<592, 256, 0, stream>>>(P, out, ns);
     return cudaGetLastError();
 }
 
-cudaError_t launch_pass(const PassParams& P, int num_sms, cudaStream_t stream)
+size_t pass_smem_bytes(const PassParams& P)
 {
+    return (size_t)kTileBytes + (size_t)2 * P.nxf * ((size_t)16 << P.log_r) + 16;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 3-D view of the source buffer: [word][row within set][set]
+static bool make_tensor_map(const PassParams& P, CUtensorMap* map)
+{
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return false;
+    const uint32_t R = 1u << P.log_r, Wt = 16384u >> P.log_r;
+    if (Wt > 256) return false;
+    const cuuint64_t row_bytes = (cuuint64_t)P.pitch4 * 16;
+    cuuint64_t gdim[3] = {(cuuint64_t)P.s4 * 4, R, P.nsets};
+    cuuint64_t gstr[2] = {(cuuint64_t)P.src_row_stride * row_bytes, P.nsets > 1 ? (cuuint64_t)P.src_set_stride * row_bytes : (cuuint64_t)P.src_row_stride * row_bytes * R};
+    cuuint32_t box[3] = {Wt, R < 256u ? R : 256u, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (gstr[0] >= (1ull << 40) || gstr[1] >= (1ull << 40)) return false;
+    CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void*)P.src, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return rc == CUDA_SUCCESS;
+}
+
+template <int LR, int NXF, int TMA>
+static cudaError_t launch_inst(const PassParams& P, const CUtensorMap& map, unsigned grid, cudaStream_t stream)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(ntt_pass_kernel<LR, NXF, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kTileBytes + 2 * NXF * (16 << LR) + 16);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    ntt_pass_kernel<LR, NXF, TMA><<<grid, kThreads, pass_smem_bytes(P), stream>>>(P, map);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pass(const PassParams& Pin, int num_sms, cudaStream_t stream)
+{
+    PassParams P = Pin;
     const uint32_t groups = (P.nstrips + P.strips_per_item - 1) / P.strips_per_item;
     const unsigned long long nitems = (unsigned long long)P.nsets * groups;
     unsigned long long grid = (unsigned long long)num_sms * 2;
     if (grid > nitems) grid = nitems;
     if (grid == 0) return cudaSuccess;
     const unsigned g = (unsigned)grid;
-    if (P.parity != ((P.log_r == 10 && P.nxf == 1) ? 1u : 0u)) return cudaErrorInvalidValue;
-#define FECC_CASE(L) case L: return P.nxf == 2 ? launch_inst<L, 2, 0>(P, g, stream) : launch_inst<L, 1, (L == 10)>(P, g, stream);
+    if (!P.tables) return cudaErrorInvalidValue;
+    CUtensorMap map;
+    memset(&map, 0, sizeof map);
+    static const bool no_tma = getenv("FASTECC_B200_NO_TMA") != nullptr;
+    const bool tma = !no_tma && P.log_r >= 6 && make_tensor_map(P, &map);
+#define FECC_CASE(L) case L: \
+        if (tma) return P.nxf == 2 ? launch_inst<L, 2, 1>(P, map, g, stream) : launch_inst<L, 1, 1>(P, map, g, stream); \
+        else     return P.nxf == 2 ? launch_inst<L, 2, 0>(P, map, g, stream) : launch_inst<L, 1, 0>(P, map, g, stream);
     switch (P.log_r) {
         FECC_CASE(5) FECC_CASE(6) FECC_CASE(7) FECC_CASE(8) FECC_CASE(9) FECC_CASE(10)
         default: return cudaErrorInvalidValue;

@@ -20,12 +20,14 @@
 //     r_i = ((j >> lb) << (lb+5)) | (i << lb) | (j & (2^lb - 1)),   i = 0..31
 // in registers, performs up to 5 stages x 16 butterflies x 2 words, and writes the slots back in place; one
 // block barrier separates rounds.  Slot r of a DIT transform initially holds input element bitrev_LR(r) and
-// finally holds output element r.
+// finally holds output element r.  Tiles arrive in natural row order (TMA box copies cannot permute rows), so the
+// FIRST transform of a tile keeps slot r at tile row bitrev_LR(r) ("bit-reversed placement") for all its rounds.
 //
-// Fused tiles (two transforms back to back, the "BC" pass of the encoder): the second transform wants its input
-// bit-reversed, i.e. its slot r' lives at tile row bitrev(r').  The 32 rows a thread holds in the LAST round of
-// the first transform (rows differing in the top five bits) are exactly the 32 slots of one thread of the FIRST
-// round of the second transform (slots differing in the low five bits), only renumbered i -> brev5(i).  So that
+// Fused tiles (two transforms back to back, the "BC" pass of the encoder): the second transform's input index
+// bitrev(r') is the first transform's output slot, which sits at tile row r' -- so the second transform runs in
+// identity placement.  The 32 rows a thread holds in the LAST round of the first transform (rows differing in
+// the low five bits) are exactly the 32 slots of one thread of the FIRST round of the second transform, only
+// renumbered i -> brev5(i).  So that
 // pair of rounds is executed back to back in registers: 18 stages of a 512-point fused tile cost 3 shared-memory
 // round trips instead of 4 (or 6 with radix-16 rounds).
 //
@@ -73,7 +75,9 @@ struct PassParams {
     uint32_t prescale;                       // multiply every input word by the constant below (1/N)
     uint32_t pw, pwhi, pwlo;
     uint32_t canonical_out;                  // reduce stored words to [0,P)
-    uint32_t parity;                         // 64-byte rows (LR == 10): swap the rows of a pair when popcount(row>>1) is odd
+    const uint4* tables;                     // per-set stage tables [set][xfi][R], built once per plan (build_tables_kernel)
+    uint32_t table_set_stride;               // uint4 entries between consecutive sets' tables (0: every set shares set 0's)
+    uint32_t use_tma;                        // 1: tile/table loads by TMA (cp.async.bulk[.tensor]) + mbarrier; 0: 16-byte cp.async
 };
 
 FECC_HD uint32_t bitrev(uint32_t x, uint32_t bits)
@@ -269,45 +273,40 @@ FECC_HD void copy16(uint4* dst_smem, const uint4* src_gmem)
 #endif
 }
 
-// Gather the heap-ordered stage table of transform xfi for row set `set` from the global power table (cp.async).
-FECC_HD void build_table(const PassParams& P, uint32_t xfi, uint32_t set, uint32_t tid, uint4* tw_s)
+// Entry idx (1 <= idx < R) of the heap-ordered stage table of transform xfi for row set `set`: an index into the
+// global power table g^e.  Used by build_tables_kernel (device) and by the CPU emulation.
+FECC_HD uint32_t table_entry_exponent(const PassParams& P, uint32_t xfi, uint32_t set, uint32_t idx)
 {
-    const uint32_t R = 1u << P.log_r;
     const Xform xf = get_xf(P, xfi);
     const uint32_t t = (xf.t0 + set * xf.t1) & (gf::M - 1);
-    for (uint32_t idx = tid; idx < R; idx += kThreads)
-        if (idx) copy16(tw_s + idx, P.tw + table_exponent(idx, P.log_r, xf.z, t));
+    return table_exponent(idx, P.log_r, xf.z, t);
 }
 
-// Issue the (asynchronous) loads of tile (set, strip).  Thread tid moves the 16 chunks c = tid + 256*m: tile row
-// p = p0 + m*2^(LR-4), whose source row is bitrev(p) = bitrev(p0) + brev4(m) -- sixteen consecutive source rows,
-// walked with one pointer increment each.
-FECC_HD void load_tile(const PassParams& P, uint32_t set, uint32_t strip, uint32_t tid, uint4* tile)
+// 16-byte cp.async fallback loader (LR == 5, or FASTECC_B200_NO_TMA=1): tile row p <- source row p of the set,
+// natural order.  Thread tid moves chunks c = tid + 256*m.
+FECC_HD void load_tile_cpasync(const PassParams& P, uint32_t set, uint32_t strip, uint32_t tid, uint4* tile)
 {
     const uint32_t LR = P.log_r, qlog = 12 - LR, Q = 1u << qlog;
     const uint32_t p0 = tid >> qlog, qq = tid & (Q - 1);
     const uint32_t gcol = strip * Q + qq;
-    if (gcol >= P.s4) return;
-    const uint32_t row0 = set * P.src_set_stride + bitrev(p0, LR) * P.src_row_stride;
-    const uint4* g = reinterpret_cast<const uint4*>(P.src) + ((size_t)row0 * P.pitch4 + gcol);
-    const size_t gstep = (size_t)P.src_row_stride * P.pitch4;
-    uint32_t cbase = (p0 << qlog) | qq;
-    if (P.parity) cbase ^= (popc32(p0 >> 1) & 1u) << qlog;
-    const uint32_t pbit = P.parity ? (1u << qlog) : 0u;
-    // four rotating source pointers: an LDGSTS keeps its address registers busy until the LSU has taken it, so
-    // reusing one pointer for consecutive copies serialises them on the long scoreboard
-    const uint4* gp[4] = {g, g + gstep, g + 2 * gstep, g + 3 * gstep};
-    const size_t gstep4 = 4 * gstep;
+    const uint32_t prow = (uint32_t)kThreads >> qlog;                 // tile rows covered by one sweep of the CTA
+    if (gcol >= P.s4) {                                               // beyond the row: keep the tile defined (TMA zero-fills)
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {                       // k = brev4(m): k-th consecutive source row
-            const int k = 4 * kk + u;
-            copy16(tile + ((cbase + 256u * (uint32_t)brev4(k)) ^ (par4(k) ? pbit : 0u)), gp[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) gp[u] += gstep4;
+        for (int m = 0; m < 16; ++m) tile[tid + (uint32_t)kThreads * m] = make_uint4(0, 0, 0, 0);
+        return;
     }
+    const uint32_t row0 = set * P.src_set_stride + p0 * P.src_row_stride;
+    const uint4* g = reinterpret_cast<const uint4*>(P.src) + ((size_t)row0 * P.pitch4 + gcol);
+    const size_t gstep = (size_t)prow * P.src_row_stride * P.pitch4;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) { copy16(tile + tid + (uint32_t)kThreads * m, g); g += gstep; }
+}
+// ... and the set's precomputed stage tables (a contiguous nxf*R*16-byte block)
+FECC_HD void load_tables_cpasync(const PassParams& P, uint32_t set, uint32_t tid, uint4* tabs)
+{
+    const uint32_t n = P.nxf << P.log_r;
+    const uint4* src = P.tables + (size_t)set * P.table_set_stride;
+    for (uint32_t i = tid; i < n; i += kThreads) copy16(tabs + i, src + i);
 }
 
 FECC_HD bool thread_active(const PassParams& P, uint32_t tid, uint32_t strip)
@@ -317,20 +316,10 @@ FECC_HD bool thread_active(const PassParams& P, uint32_t tid, uint32_t strip)
     return (words2 >> 1) < P.s4;                                    // partial last strip: beyond the row's last chunk
 }
 
-// Tile address (in uint2 units) of the thread's slot i in round c:  physical row = slot (first transform, and the
-// fused step) or bitrev(slot) (later rounds of the second transform); the rows of a pair are swapped by popcount
-// parity when P.parity.  All variants reduce to "base + i*step" (or base ^ const): one ALU instruction per access.
+// Tile address (in uint2 units) of the thread's slot i in round c:  physical row = bitrev(slot) for the first
+// transform of a tile (brev), = slot for the second.  Both reduce to "base + i*step" with compile-time i.
 #define FECC_SLOT_LOOP(ACCESS)                                                                                     \
-    if (P.parity) {                    /* identity placement only: plan.h never combines parity with a fused tile */ \
-        if (c.lb == 0) {                                                                                           \
-            const uint32_t B = ((tp.j << 8) | tp.q2) ^ ((popc32(tp.j) & 1u) << 3);                                 \
-            _Pragma("unroll") for (int i = 0; i < kRows; ++i) { const uint32_t a = B ^ (uint32_t)((i ^ (int)par5(i >> 1)) << 3); ACCESS(i, a); } \
-        } else {                                                                                                   \
-            uint32_t a0 = ((c.jbase ^ (popc32(c.jbase >> 1) & 1u)) << 3) | tp.q2;                                  \
-            const uint32_t step = 8u << c.lb;                                                                      \
-            _Pragma("unroll") for (int i = 0; i < kRows; ++i) { const uint32_t a = a0 ^ (par5(i) << 3); ACCESS(i, a); a0 += step; } \
-        }                                                                                                          \
-    } else if (brev) {                                                                                             \
+    if (brev) {                                                                                                    \
         uint32_t a = (bitrev(c.jbase, LR) << tp.q2log) | tp.q2;                                                    \
         const uint32_t step = 1u << (LR - kStages - c.lb + tp.q2log);                                              \
         _Pragma("unroll") for (int k = 0; k < kRows; ++k) { ACCESS(brev5(k), a); a += step; }                      \
@@ -340,7 +329,7 @@ FECC_HD bool thread_active(const PassParams& P, uint32_t tid, uint32_t strip)
         _Pragma("unroll") for (int i = 0; i < kRows; ++i) { ACCESS(i, a); a += step; }                             \
     }
 
-// (a) read the thread's 32 slots of a step.  brev = bit-reversed placement (rounds >= 1 of the second transform).
+// (a) read the thread's 32 slots of a step.  brev = bit-reversed placement (every round of the FIRST transform).
 FECC_HD void round_read(const PassParams& P, uint32_t k, uint32_t brev, uint32_t tid, const uint4* tile, RoundRegs& r)
 {
     const uint32_t LR = P.log_r;
@@ -387,20 +376,33 @@ FECC_HD void round_write_tile(const PassParams& P, uint32_t k, uint32_t brev, ui
 }
 
 // ... or (last step) store output element r to its global row.  After a fused step that is also the last step
-// (LR <= 5) register brev5(i) holds output element i of the second transform.
+// (LR <= 5) register brev5(i) holds output element i of the second transform.  Eight rotating pointers whose
+// increments are hidden from the optimiser: a store keeps its address registers busy until the LSU has taken
+// it, so one incrementing pointer would serialise the 32 stores on the long scoreboard.
+FECC_HD void opaque_advance(uint2*& p, size_t bytes)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("add.u64 %0, %0, %1;" : "+l"(p) : "l"(bytes));
+#else
+    p = reinterpret_cast<uint2*>(reinterpret_cast<char*>(p) + bytes);
+#endif
+}
 FECC_HD void round_write_global(const PassParams& P, const Step st, uint32_t tid, uint32_t set, uint32_t strip, const RoundRegs& r)
 {
     const ThreadPos tp = thread_pos(P.log_r, tid);
     const RoundCtx c = st.fused ? make_round(P.log_r, 0, 0) : make_round(P.log_r, st.k, tp.j);
     const uint32_t gcol2 = strip * (8192u >> P.log_r) + tp.q2;
     const uint32_t row0 = set * P.dst_set_stride + c.jbase * P.dst_row_stride;
-    uint2* g = reinterpret_cast<uint2*>(P.dst) + ((size_t)row0 * P.pitch4 * 2 + gcol2);
-    const size_t gstep = ((size_t)P.dst_row_stride * P.pitch4 * 2) << c.lb;
+    uint2* g0 = reinterpret_cast<uint2*>(P.dst) + ((size_t)row0 * P.pitch4 * 2 + gcol2);
+    const size_t gstep = (((size_t)P.dst_row_stride * P.pitch4 * 2) << c.lb) * sizeof(uint2);      // bytes between slots
+    uint2* gp[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { gp[u] = g0; opaque_advance(gp[u], gstep * u); }
 #pragma unroll
     for (int i = 0; i < kRows; ++i) {
         const uint2 v = st.fused ? r.x[brev5(i)] : r.x[i];
-        *g = P.canonical_out ? canon2(v) : v;
-        g += gstep;
+        *gp[i & 7] = P.canonical_out ? canon2(v) : v;
+        if (i + 8 < kRows) opaque_advance(gp[i & 7], gstep * 8);
     }
 }
 

@@ -43,7 +43,6 @@ inline PassParams base_pass(const Buffers& b, uint32_t log_r)
     p.nstrips = (p.s4 + Q - 1) / Q;
     p.strips_per_item = p.nstrips >= 16 ? 4 : 1;
     p.nxf = 1;
-    p.parity = (log_r == 10) ? 1u : 0u;
     return p;
 }
 
@@ -95,7 +94,6 @@ inline std::vector<PassParams> plan_encode(const Buffers& b, size_t N)
         a.src = b.x; a.dst = b.x; a.nsets = 1;
         a.src_set_stride = a.dst_set_stride = 0; a.src_row_stride = a.dst_row_stride = 1;
         a.nxf = 2;
-        a.parity = 0;                                                   // bit-reversed placement between the two transforms
         a.xf[0] = Xform{emod(-2 * q), 0, 0};
         a.xf[1] = Xform{emod(2 * q), emod(q), 0};
         a.prescale = 1; a.pw = invN.w; a.pwhi = invN.whi; a.pwlo = invN.wlo;
@@ -115,7 +113,6 @@ inline std::vector<PassParams> plan_encode(const Buffers& b, size_t N)
     bc.src = b.x; bc.dst = b.x; bc.nsets = (uint32_t)N1;
     bc.src_set_stride = bc.dst_set_stride = N2; bc.src_row_stride = bc.dst_row_stride = 1;
     bc.nxf = 2;
-    bc.parity = 0;
     bc.xf[0] = Xform{emod(-2 * q * (long long)N1), 0, emod(-2 * q)};
     bc.xf[1] = Xform{emod(2 * q * (long long)N1), emod(q * (long long)N1), 0};
     v.push_back(bc);
@@ -127,6 +124,15 @@ inline std::vector<PassParams> plan_encode(const Buffers& b, size_t N)
     v.push_back(d);
     return v;
 }
+
+// Per-set stage tables of a pass: [set][xfi][R] entries of 16 bytes; a single shared set when no twist depends on it.
+inline uint32_t table_sets(const PassParams& P)
+{
+    bool varies = false;
+    for (uint32_t x = 0; x < P.nxf; ++x) if (P.xf[x].t1) varies = true;
+    return varies ? P.nsets : 1u;
+}
+inline size_t table_bytes(const PassParams& P) { return (size_t)table_sets(P) * P.nxf * ((size_t)16 << P.log_r); }
 
 // g^e table, e in [0, 2^20): 16 MiB, L2-resident on the device.
 inline void fill_power_table(gf::Tw* t)
