@@ -54,24 +54,18 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-struct TileIter {                       // the CTA's walk over (item -> strips)
-    uint32_t item, set, strip, strip_end;
-};
-__device__ __forceinline__ bool iter_decode(const PassParams& P, uint32_t groups, uint32_t nitems, TileIter& it)
+// The CTA's t-th tile.  Work items (a row set x strips_per_item consecutive strips) are dealt round-robin to the
+// CTAs; plan.h guarantees strips_per_item divides nstrips, so tile t of a CTA is strip (t % spi) of its (t / spi)-th item.
+__device__ __forceinline__ bool tile_decode(const PassParams& P, uint32_t groups, uint32_t nitems, uint32_t t, uint32_t& set, uint32_t& strip)
 {
-    if (it.item >= nitems) return false;
-    it.set = it.item / groups;
-    const uint32_t sg = it.item - it.set * groups;
-    it.strip = sg * P.strips_per_item;
-    it.strip_end = min(it.strip + P.strips_per_item, P.nstrips);
+    const uint32_t spi = P.strips_per_item;
+    const uint32_t item = blockIdx.x + (t / spi) * gridDim.x;
+    if (item >= nitems) return false;
+    set = item / groups;
+    strip = (item - set * groups) * spi + (t % spi);
     return true;
 }
-__device__ __forceinline__ bool iter_next(const PassParams& P, uint32_t groups, uint32_t nitems, TileIter& it)
-{
-    if (++it.strip < it.strip_end) return true;
-    it.item += gridDim.x;
-    return iter_decode(P, groups, nitems, it);
-}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory"); }
 
 // LR / NXF / TMA are compile-time: the kernel patches them into its copy of the parameters, so every shift, stride
 // and placement branch in ntt_tile.cuh folds to an immediate (keeps the 64 data registers from spilling).
@@ -95,10 +89,11 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(const PassParams 
     constexpr uint32_t kBoxes = R / kRowsBox;
     constexpr uint32_t kTableBytes = NXF * R * 16u;
 
-    TileIter cur; cur.item = blockIdx.x;
-    if (!iter_decode(P, groups, nitems, cur)) return;
+    uint32_t cur_set, cur_strip;
+    if (!tile_decode(P, groups, nitems, 0, cur_set, cur_strip)) return;
     uint32_t tb = 0;                                      // table buffer used by the current tile
     uint32_t phase = 0;
+    uint64_t* rbar = bar + 1;                             // "all eight warps have pulled the last step's slots into registers"
 
     // request tile (set, strip) [+ the set's tables into buffer tbuf]
     auto request = [&](uint32_t set, uint32_t strip, bool with_tables, uint32_t tbuf) {
@@ -119,41 +114,50 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(const PassParams 
     };
 
     if (TMA) {
-        if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+        if (tid == 0) { mbar_init(bar, 1); mbar_init(rbar, kThreads / 32); fence_mbar_init(); }
         __syncthreads();
     }
-    request(cur.set, cur.strip, true, tb);                // prologue: first tile + its tables
+    request(cur_set, cur_strip, true, tb);                // prologue: first tile + its tables
 
-    for (;;) {
-        if (TMA) { mbar_wait(bar, phase); phase ^= 1u; }
+    for (uint32_t t = 0;; ++t) {
+        if (TMA) mbar_wait(bar, phase);
         else     { cp_async_wait_all(); __syncthreads(); }
-        const bool active = thread_active(P, tid, cur.strip);
-        const uint4* tw0 = tabs + (tb * NXF) * R;
-        const uint4* tw1 = tw0 + R;
+        const bool active = thread_active(P, tid, cur_strip);
         RoundRegs r;
-        TileIter nxt = cur;
-        bool has_next = false;
 #pragma unroll 1
         for (uint32_t s = 0; s < nsteps; ++s) {
             const Step st = step_of(LR, NXF, s);
             const bool last = s + 1 == nsteps;
             if (active) round_read(P, st.k, st.xfi == 0, tid, tile, r);
-            if (last) {
-                __syncthreads();                          // every slot is in registers: the tile buffer is free
-                has_next = iter_next(P, groups, nitems, nxt);
-                if (has_next) request(nxt.set, nxt.strip, nxt.set != cur.set, tb ^ 1u);   // flies under the last step's butterflies
+            if (last) {                                   // every slot is in registers: the tile buffer is free.
+                if (TMA) {                                // each warp reports in; only the issuing thread waits for all of them
+                    __syncwarp();
+                    if ((tid & 31) == 0) mbar_arrive(rbar);
+                    if (tid == 0) {                       // the next tile flies under the last step's butterflies
+                        mbar_wait(rbar, phase);
+                        uint32_t ns, nst;
+                        if (tile_decode(P, groups, nitems, t + 1, ns, nst)) request(ns, nst, ns != cur_set, tb ^ 1u);
+                    }
+                } else {
+                    __syncthreads();
+                    uint32_t ns, nst;
+                    if (tile_decode(P, groups, nitems, t + 1, ns, nst)) request(ns, nst, ns != cur_set, tb ^ 1u);
+                }
             }
-            if (active) round_math(P, st, tid, cur.set, tw0, tw1, r, zero);
+            const uint4* tw0 = tabs + (tb * NXF) * R;
+            if (active) round_math(P, st, tid, cur_set, tw0, tw0 + R, r, zero);
             if (!last) {
                 if (active) round_write_tile(P, st.k, st.xfi == 0, tid, tile, r);
                 __syncthreads();
             } else if (active) {
-                round_write_global(P, st, tid, cur.set, cur.strip, r);
+                round_write_global(P, st, tid, cur_set, cur_strip, r);
             }
         }
-        if (!has_next) break;
-        if (nxt.set != cur.set) tb ^= 1u;
-        cur = nxt;
+        uint32_t nxt_set, nxt_strip;                      // (re)decoded here, where registers are plentiful
+        if (!tile_decode(P, groups, nitems, t + 1, nxt_set, nxt_strip)) break;
+        phase ^= 1u;
+        if (nxt_set != cur_set) tb ^= 1u;
+        cur_set = nxt_set; cur_strip = nxt_strip;
     }
 }
 
@@ -181,7 +185,7 @@ cudaError_t launch_build_tables(PassParams& P, uint4* out, cudaStream_t stream)
 
 size_t pass_smem_bytes(const PassParams& P)
 {
-    return (size_t)kTileBytes + (size_t)2 * P.nxf * ((size_t)16 << P.log_r) + 16;
+    return (size_t)kTileBytes + (size_t)2 * P.nxf * ((size_t)16 << P.log_r) + 16;   // + two mbarriers
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

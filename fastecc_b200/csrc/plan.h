@@ -41,7 +41,7 @@ inline PassParams base_pass(const Buffers& b, uint32_t log_r)
     p.log_r = log_r;
     const uint32_t Q = 4096u >> log_r;                                  // 16-byte chunks per tile row
     p.nstrips = (p.s4 + Q - 1) / Q;
-    p.strips_per_item = p.nstrips >= 16 ? 4 : 1;
+    p.strips_per_item = (p.nstrips >= 16 && p.nstrips % 4 == 0) ? 4 : 1;   // must divide nstrips (ntt_pass.cu tile_decode)
     p.nxf = 1;
     return p;
 }
