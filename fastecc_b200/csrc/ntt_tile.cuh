@@ -387,10 +387,20 @@ FECC_HD void opaque_advance(uint2*& p, size_t bytes)
     p = reinterpret_cast<uint2*>(reinterpret_cast<char*>(p) + bytes);
 #endif
 }
-FECC_HD void round_write_global(const PassParams& P, const Step st, uint32_t tid, uint32_t set, uint32_t strip, const RoundRegs& r)
+FECC_HD void store_global2(uint2* p, uint2 v)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("st.global.v2.u32 [%0], {%1, %2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");   // the opaque pointer arithmetic hides the address space
+#else
+    *p = v;
+#endif
+}
+FECC_HD void round_write_global(const PassParams& P, const Step st, uint32_t tid, uint32_t set, uint32_t strip, RoundRegs& r)
 {
     const ThreadPos tp = thread_pos(P.log_r, tid);
-    const RoundCtx c = st.fused ? make_round(P.log_r, 0, 0) : make_round(P.log_r, st.k, tp.j);
+    // the last step is the fused one only when a fused tile has a single round (LR <= 5): compile-time in the kernel
+    const bool fused_last = (P.nxf == 2) && (num_rounds(P.log_r) == 1);
+    const RoundCtx c = fused_last ? make_round(P.log_r, 0, 0) : make_round(P.log_r, st.k, tp.j);
     const uint32_t gcol2 = strip * (8192u >> P.log_r) + tp.q2;
     const uint32_t row0 = set * P.dst_set_stride + c.jbase * P.dst_row_stride;
     uint2* g0 = reinterpret_cast<uint2*>(P.dst) + ((size_t)row0 * P.pitch4 * 2 + gcol2);
@@ -398,10 +408,13 @@ FECC_HD void round_write_global(const PassParams& P, const Step st, uint32_t tid
     uint2* gp[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) { gp[u] = g0; opaque_advance(gp[u], gstep * u); }
+    // every pass stores canonical residues (two ALU instructions per word, in place): only the last pass needs it,
+    // but a run-time choice would cost a select and a register copy per word in front of each store
 #pragma unroll
     for (int i = 0; i < kRows; ++i) {
-        const uint2 v = st.fused ? r.x[brev5(i)] : r.x[i];
-        *gp[i & 7] = P.canonical_out ? canon2(v) : v;
+        const int reg = fused_last ? brev5(i) : i;
+        r.x[reg] = canon2(r.x[reg]);
+        store_global2(gp[i & 7], r.x[reg]);
         if (i + 8 < kRows) opaque_advance(gp[i & 7], gstep * 8);
     }
 }
