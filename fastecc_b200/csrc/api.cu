@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdarg>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 #include <atomic>
@@ -36,7 +37,9 @@ struct Context {
     DevBuf packed;       // repacked copy for unaligned device layouts
     DevBuf staging;      // device copy for the host (T**) entry points
     std::map<uint32_t, std::vector<DevBuf>> tables;   // per (mode, log2 N): one table block per pass (plan.h table_bytes)
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // compute
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_done;
 };
 
 Context* g_ctx = nullptr;
@@ -131,6 +134,29 @@ int run_host(uint32_t** data, size_t N, size_t size, int mode, const char* who)
     bool contiguous = true;
     for (size_t i = 1; i < N; i++) if (data[i] != data[0] + i * size) { contiguous = false; break; }
     if (pitch != size) CUDA_TRY(cudaMemsetAsync(dv, 0, N * pitch * sizeof(uint32_t), st));
+    // Large contiguous arrays: the word columns are independent codewords, so the array is cut into column chunks and
+    // H2D(chunk c+1), the transform of chunk c and D2H(chunk c-1) run concurrently on three streams (PCIe is full duplex).
+    static const size_t chunk_env = getenv("FASTECC_B200_CHUNK_WORDS") ? (size_t)atol(getenv("FASTECC_B200_CHUNK_WORDS")) : 0;
+    size_t cw = chunk_env ? (chunk_env + 15) / 16 * 16 : 128;
+    const bool pipelined = contiguous && pitch == size && size >= 2 * cw && N * size * 4 >= ((size_t)32 << 20);
+    if (pipelined) {
+        const size_t nchunks = (size + cw - 1) / cw;
+        while (c->ev_in.size() < nchunks) { cudaEvent_t e; CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->ev_in.push_back(e); }
+        while (c->ev_done.size() < nchunks) { cudaEvent_t e; CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->ev_done.push_back(e); }
+        for (size_t k = 0; k < nchunks; ++k) {
+            const size_t c0 = k * cw, w = (c0 + cw <= size) ? cw : size - c0;
+            CUDA_TRY(cudaMemcpy2DAsync(dv + c0, pitch * 4, data[0] + c0, size * 4, w * 4, N, cudaMemcpyHostToDevice, c->h2d));
+            CUDA_TRY(cudaEventRecord(c->ev_in[k], c->h2d));
+            CUDA_TRY(cudaStreamWaitEvent(st, c->ev_in[k], 0));
+            if (int rc = run_aligned(c, dv + c0, N, w, pitch, mode, st)) return rc;
+            CUDA_TRY(cudaEventRecord(c->ev_done[k], st));
+            CUDA_TRY(cudaStreamWaitEvent(c->d2h, c->ev_done[k], 0));
+            CUDA_TRY(cudaMemcpy2DAsync(data[0] + c0, size * 4, dv + c0, pitch * 4, w * 4, N, cudaMemcpyDeviceToHost, c->d2h));
+        }
+        CUDA_TRY(cudaStreamSynchronize(c->d2h));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return 0;
+    }
     if (contiguous) {
         CUDA_TRY(cudaMemcpy2DAsync(dv, pitch * 4, data[0], size * 4, size * 4, N, cudaMemcpyHostToDevice, st));
     } else {
@@ -169,6 +195,8 @@ int fastecc_b200_init(int device)
     CUDA_TRY(cudaMalloc((void**)&c->d_tw, sizeof(gf::Tw) * gf::M));
     CUDA_TRY(cudaMemcpy(c->d_tw, tw.data(), sizeof(gf::Tw) * gf::M, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
     g_ctx = c;
     return 0;
 }
@@ -183,6 +211,10 @@ void fastecc_b200_shutdown(void)
     for (auto& kv : g_ctx->tables) for (auto& b : kv.second) b.release();
     if (g_ctx->d_tw) cudaFree(g_ctx->d_tw);
     if (g_ctx->stream) cudaStreamDestroy(g_ctx->stream);
+    if (g_ctx->h2d) cudaStreamDestroy(g_ctx->h2d);
+    if (g_ctx->d2h) cudaStreamDestroy(g_ctx->d2h);
+    for (auto e : g_ctx->ev_in) cudaEventDestroy(e);
+    for (auto e : g_ctx->ev_done) cudaEventDestroy(e);
     delete g_ctx; g_ctx = nullptr;
 }
 
