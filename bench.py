@@ -122,10 +122,9 @@ def cpu_encode_runner(log_n, size_words):
     buf = (np.arange(N * size_words, dtype=np.uint64) % P).astype(np.uint32)
     r = load_ref_lib()
     if r is not None:
-        tab = (ctypes.c_void_p * N)()                   # T** data, RS.cpp:31-33; left permuted between steps like the reference leaves it
-        for i in range(N):
-            tab[i] = buf.ctypes.data + i * size_words * 4
-        return (lambda _keep=buf: r.ref_rs_encode(tab, N, size_words)), "reference", int(r.ref_num_threads()), \
+        # T** data, RS.cpp:31-33; left permuted between steps like the reference leaves it
+        tab = buf.ctypes.data + np.arange(N, dtype=np.uint64) * np.uint64(size_words * 4)
+        return (lambda _keep=buf: r.ref_rs_encode(tab.ctypes.data, N, size_words)), "reference", int(r.ref_num_threads()), \
             "unmodified FastECC templates, %s+OpenMP build (oracle/_ref)" % r.ref_build_flavour().decode()
     o = load_oracle_port()
     return (lambda: o.oracle_rs_encode(buf.ctypes.data, N, size_words)), "port", int(o.oracle_num_threads()), "oracle/gfp_oracle.c (plain C port, OpenMP)"
@@ -136,6 +135,7 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     os.environ.setdefault("OMP_WAIT_POLICY", "active")
+    os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))      # torchrun pins it to 1: the reference gets every host thread
     size_words = args.block_bytes // 4
     N = 1 << args.log_n
     fn, kind, cores, label = cpu_encode_runner(args.log_n, size_words)
@@ -168,6 +168,7 @@ def quick_cpu_baseline(args):
     """Bounded CPU sample for the own arm's cpu_baseline block: a few full encodes (about 10-30 s of CPU work at most)."""
     try:
         os.environ.setdefault("OMP_WAIT_POLICY", "active")
+        os.environ.setdefault("OMP_NUM_THREADS", str(len(os.sched_getaffinity(0))))
         size_words = args.block_bytes // 4
         fn, kind, cores, label = cpu_encode_runner(args.log_n, size_words)
         fn()

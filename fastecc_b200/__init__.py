@@ -105,16 +105,14 @@ Blocks = Union[np.ndarray, Sequence[np.ndarray]]
 
 def _pointer_table(data: Blocks, N: int, SIZE: int):
     """Build the reference's ``T** data`` (RS.cpp:31-33) for a 2-D array or a sequence of block arrays."""
-    tab = (ctypes.c_void_p * N)()
     if isinstance(data, np.ndarray):
         if data.dtype != np.uint32 or data.ndim != 2 or data.shape != (N, SIZE) or not data.flags.c_contiguous or not data.flags.writeable:
             raise ValueError("data must be a writeable C-contiguous uint32 array of shape (N, SIZE)")
-        base = data.ctypes.data
-        for i in range(N):
-            tab[i] = base + i * SIZE * 4
+        tab = data.ctypes.data + np.arange(N, dtype=np.uint64) * np.uint64(SIZE * 4)      # data[i] = data0 + i*SIZE
         return tab, data
     if len(data) != N:
         raise ValueError("len(data) != N")
+    tab = np.empty(N, dtype=np.uint64)
     for i, blk in enumerate(data):
         if blk.dtype != np.uint32 or blk.ndim != 1 or blk.shape[0] < SIZE or not blk.flags.c_contiguous or not blk.flags.writeable:
             raise ValueError(f"block {i} must be a writeable contiguous uint32 vector of >= SIZE words")
@@ -125,14 +123,14 @@ def _pointer_table(data: Blocks, N: int, SIZE: int):
 def MFA_NTT(data: Blocks, N: int, SIZE: int, InvNTT: bool) -> None:
     """In-place length-N NTT of every word column (unnormalised inverse), bit-exact with ntt.cpp:382-447."""
     tab, keep = _pointer_table(data, N, SIZE)
-    _check(lib().fastecc_b200_ntt_u32(ctypes.cast(tab, ctypes.c_void_p), N, SIZE, 1 if InvNTT else 0))
+    _check(lib().fastecc_b200_ntt_u32(tab.ctypes.data, N, SIZE, 1 if InvNTT else 0))
     del keep
 
 
 def EncodeReedSolomon_body(data: Blocks, N: int, SIZE: int) -> None:
     """N data blocks -> N parity blocks in place: MFA_NTT(inv); x[i] *= root_2N^i/N; MFA_NTT(fwd)  (RS.cpp:41-63)."""
     tab, keep = _pointer_table(data, N, SIZE)
-    _check(lib().fastecc_b200_rs_encode(ctypes.cast(tab, ctypes.c_void_p), N, SIZE))
+    _check(lib().fastecc_b200_rs_encode(tab.ctypes.data, N, SIZE))
     del keep
 
 
