@@ -233,10 +233,8 @@ def run_b200_arm(args):
     ms = ev0.elapsed_time(ev1)
     launches = fe.kernel_launches() - launches0
     clocks = sampler.stop() if sampler else None
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    from fastecc_b200 import multirank
+    ms = multirank.max_over_ranks(ms, device=dev)          # a multi-GPU step takes as long as its slowest rank
     barrier()
 
     # ---- end-to-end through the reference-facing host call (T** table, pinned host memory, H2D + D2H inside)
@@ -254,10 +252,7 @@ def run_b200_arm(args):
             fe.EncodeReedSolomon_body(harr, N, S)
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
+        e2e_s = multirank.max_over_ranks(e2e_s, device=dev)
         e2e = {"value": world * nbytes * args.e2e_steps / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": N * S * 4, "d2h_bytes_per_step": N * S * 4,
                "ms_per_step": 1e3 * e2e_s / args.e2e_steps, "api": "fastecc_b200_rs_encode(T** data, N, SIZE) on pinned host blocks"}
         del harr
