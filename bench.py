@@ -28,6 +28,25 @@ P = 0xFFF00001
 METRIC = "rs_encode_GBps_n2^20_k2^19_4KiB_blocks"
 
 
+def profiled_traffic():
+    """DRAM bytes (read + write) per ntt_pass_kernel launch from the committed `ncu --set full` capture of this workload
+    (profiles/*_passes_A_BC_D.csv, newest), averaged over the three passes of an encode; None if absent."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_v*_passes_A_BC_D.csv")), key=os.path.getmtime)
+    if not files:
+        return None, None
+    try:
+        rows = list(csv.reader(open(files[-1])))
+        h, units, data = rows[0], rows[1], rows[2:]
+        ir, iw = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        tot = [float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]] for r in data]
+        return sum(tot) / len(tot), os.path.basename(files[-1])
+    except Exception:
+        return None, None
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -260,6 +279,7 @@ def run_b200_arm(args):
 
     if rank == 0:
         peak, peak_src = measured_peak()
+        traffic, traffic_src = profiled_traffic() if (args.log_n == 19 and args.block_bytes == 4096) else (None, None)
         passes_per_step = launches / max(args.steps, 1)
         launch_ms = ms / max(launches, 1)
         achieved = nbytes / (launch_ms * 1e-3) / 1e9              # every pass reads and writes the whole array once
@@ -272,7 +292,7 @@ def run_b200_arm(args):
                        "l2": "inputs (2 GiB per GPU) are larger than L2; no flush needed", "parallelism": "independent stripe per GPU" if world > 1 else "single GPU",
                        "passes_per_encode": passes_per_step},
             "roofline": {"bound": "hbm", "kernel": "ntt_pass_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "note": "algorithmic bytes per launch = 2*N*SIZE*4 (one read + one write of the array per pass); avg launch = timed region / launches"},
             "gpu_launches": int(launches),
             "clocks": clocks,

@@ -239,7 +239,8 @@ cudaError_t launch_pass(const PassParams& Pin, int num_sms, cudaStream_t stream)
     PassParams P = Pin;
     const uint32_t groups = (P.nstrips + P.strips_per_item - 1) / P.strips_per_item;
     const unsigned long long nitems = (unsigned long long)P.nsets * groups;
-    unsigned long long grid = (unsigned long long)num_sms * 2;
+    static const int ctas_per_sm = getenv("FASTECC_B200_CTAS_PER_SM") ? atoi(getenv("FASTECC_B200_CTAS_PER_SM")) : 2;   // tuning knob
+    unsigned long long grid = (unsigned long long)num_sms * (ctas_per_sm > 0 ? ctas_per_sm : 2);
     if (grid > nitems) grid = nitems;
     if (grid == 0) return cudaSuccess;
     const unsigned g = (unsigned)grid;
