@@ -58,6 +58,8 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--mode", default="stripes", choices=["stripes", "sharded"],
+                    help="multi-GPU: independent stripe per GPU (default, weak scaling) or ONE transform sharded over the GPUs with two NCCL all-to-alls (strong scaling, BASELINE config 4)")
     return ap.parse_args()
 
 
@@ -220,6 +222,8 @@ def run_b200_arm(args):
 
     N, S = 1 << args.log_n, args.block_bytes // 4
     dev = torch.device("cuda", local)
+    if args.mode == "sharded" and world > 1:
+        return run_sharded(args, fe, rank, world, local, dev)
     data = torch.empty((N, S), dtype=torch.int32, device=dev)
     flat = data.view(-1)
     step_elems = 1 << 26
@@ -304,6 +308,59 @@ def run_b200_arm(args):
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    return 0
+
+
+def run_sharded(args, fe, rank, world, local, dev):
+    """ONE encode of 2^log_n blocks sharded over the ranks: local passes + two all-to-alls (fastecc_b200/sharded.py)."""
+    import torch
+    import torch.distributed as dist
+    from fastecc_b200 import multirank, sharded
+    N, S = 1 << args.log_n, args.block_bytes // 4
+    rows = N // world
+    x = (torch.arange(rows * S, device=dev, dtype=torch.int64) * 2654435761 % P).to(torch.int32).view(rows, S)
+    run_pass = sharded.gpu_pass_runner(N, world, rank)
+    nbytes = 2.0 * N * S * 4
+
+    def sync():
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        x = sharded.rs_encode_sharded(x, N, world, run_pass)
+    sync()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start(); time.sleep(0.25)
+    launches0 = fe.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    ev0.record()
+    for _ in range(args.steps):
+        x = sharded.rs_encode_sharded(x, N, world, run_pass)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = multirank.max_over_ranks(ev0.elapsed_time(ev1), device=dev)
+    launches = fe.kernel_launches() - launches0
+    clocks = sampler.stop() if sampler else None
+    sync()
+    if rank == 0:
+        a2a_bytes = 2.0 * (world - 1) / world * (N * S * 4 / world)           # sent per GPU per encode (two all-to-alls)
+        link = 770.0                                                          # GB/s per direction per GPU, measured peer copy (B200_PROFILING.md)
+        t_link = a2a_bytes / (link * 1e9)
+        out = {
+            "metric": METRIC, "value": nbytes * args.steps / (ms * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": "rs_encode N=2^%d data blocks -> 2^%d parity, %d-byte blocks, ONE transform sharded over %d GPUs" % (args.log_n, args.log_n, args.block_bytes, world),
+                       "bytes_per_step": nbytes, "convention": "2*N*SIZE*4 bytes per encode (RS.cpp:38)", "parallelism": "cyclic blocks, 3 local passes + 2 NCCL all-to-all",
+                       "l2": "local arrays (%.0f MiB per GPU) exceed L2" % (N * S * 4 / world / 2**20)},
+            "roofline": {"bound": "nvlink", "achieved": a2a_bytes / (ms / args.steps * 1e-3) / 1e9, "peak": link, "unit": "GB/s",
+                         "frac": t_link / (ms / args.steps * 1e-3), "traffic": None,
+                         "note": "all-to-all bytes sent per GPU per encode / step time, against the measured 770 GB/s per-direction peer bandwidth"},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(out), flush=True)
+    dist.destroy_process_group()
     return 0
 
 

@@ -51,6 +51,7 @@ def lib() -> ctypes.CDLL:
         L.fastecc_b200_rs_encode.argtypes = [vp, sz, sz]; L.fastecc_b200_rs_encode.restype = ci
         L.fastecc_b200_ntt_u32_dev.argtypes = [vp, sz, sz, sz, ci, vp]; L.fastecc_b200_ntt_u32_dev.restype = ci
         L.fastecc_b200_rs_encode_dev.argtypes = [vp, sz, sz, sz, vp]; L.fastecc_b200_rs_encode_dev.restype = ci
+        L.fastecc_b200_rs_encode_shard_pass.argtypes = [vp, sz, ci, ci, sz, sz, ci, vp]; L.fastecc_b200_rs_encode_shard_pass.restype = ci
         L.fastecc_b200_kernel_launches.argtypes = []; L.fastecc_b200_kernel_launches.restype = ctypes.c_ulonglong
         L.fastecc_b200_host_alloc.argtypes = [sz]; L.fastecc_b200_host_alloc.restype = vp
         L.fastecc_b200_host_free.argtypes = [vp]; L.fastecc_b200_host_free.restype = None

@@ -229,6 +229,30 @@ int fastecc_b200_ntt_u32_dev(uint32_t* d, size_t N, size_t size, size_t pitch, i
 int fastecc_b200_rs_encode_dev(uint32_t* d, size_t N, size_t size, size_t pitch, void* stream)
 { return run_dev(d, N, size, pitch, 2, stream, "fastecc_b200_rs_encode_dev"); }
 
+int fastecc_b200_rs_encode_shard_pass(uint32_t* d_local, size_t N, int n_ranks, int rank, size_t size, size_t pitch, int which, void* stream)
+{
+    const char* who = "fastecc_b200_rs_encode_shard_pass";
+    Context* c = g_ctx;
+    if (!c) return fail(FASTECC_B200_ENOINIT, "%s: call fastecc_b200_init() first", who);
+    if (!d_local || which < 0 || which > 2 || rank < 0 || rank >= n_ranks) return fail(FASTECC_B200_EINVAL, "%s: bad arguments", who);
+    if (!shard_supported(N, (uint32_t)n_ranks)) return fail(FASTECC_B200_EINVAL, "%s: N=%zu cannot be sharded over %d ranks (need a power of two 2^11..2^19 with N2 %% ranks == 0)", who, N, n_ranks);
+    if (size == 0 || pitch < size || pitch % 4 || ((uintptr_t)d_local) % 16) return fail(FASTECC_B200_EINVAL, "%s: needs SIZE >= 1, a 16-byte aligned buffer and pitch %% 4 == 0", who);
+    if ((unsigned long long)(N / n_ranks) * (pitch / 4) >= (1ull << 32)) return fail(FASTECC_B200_EINVAL, "%s: local buffer too large", who);
+    cudaStream_t st = (cudaStream_t)stream;
+    Buffers b{d_local, nullptr, c->d_tw, (uint32_t)pitch, (uint32_t)size};
+    PassParams p = plan_encode_shard(b, N, (uint32_t)n_ranks, (uint32_t)rank, which);
+    std::vector<DevBuf>& tabs = c->tables[0x80000000u | (uint32_t)n_ranks << 16 | (uint32_t)rank << 8 | ilog2(N)];
+    if (tabs.empty()) tabs.resize(3);
+    if (!tabs[which].p) {
+        CUDA_TRY(tabs[which].reserve(table_bytes(p)));
+        CUDA_TRY(launch_build_tables(p, (uint4*)tabs[which].p, st)); g_launches++;
+    }
+    p.tables = (const uint4*)tabs[which].p;
+    p.table_set_stride = table_sets(p) > 1 ? (p.nxf << p.log_r) : 0u;
+    CUDA_TRY(launch_pass(p, c->num_sms, st)); g_launches++;
+    return 0;
+}
+
 int fastecc_b200_ntt_u32(uint32_t** data, size_t N, size_t size, int inverse)
 { return run_host(data, N, size, inverse ? 1 : 0, "fastecc_b200_ntt_u32"); }
 

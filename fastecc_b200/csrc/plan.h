@@ -125,6 +125,55 @@ inline std::vector<PassParams> plan_encode(const Buffers& b, size_t N)
     return v;
 }
 
+// One transform sharded over G GPUs (BASELINE config 4).  Blocks are dealt cyclically: global block
+// i = l*G + g is local block l of rank g, for the data going in and for the parity coming out.  With N2 % G == 0 every
+// row set of pass A (fixed n2) and of pass D (fixed j2) is local to rank n2 % G resp. j2 % G, and every row set of
+// pass BC (fixed k1) is local to rank k1 % G after an all-to-all of whole blocks (fastecc_b200/sharded.py).  The local
+// passes are the single-GPU ones with local strides; the only thing that knows about the sharding is the twist,
+// whose exponent t0 + set*t1 is evaluated at the GLOBAL set index set_local*G + rank.
+//   which = 0: A  on local rows n1*(N2/G) + n2'            (n2 = n2'*G + rank)
+//   which = 1: BC on local rows k1'*N2 + n2                (k1 = k1'*G + rank)
+//   which = 2: D  on local rows k1*(N2/G) + j2'            (j2 = j2'*G + rank)
+inline bool shard_supported(size_t N, uint32_t G)
+{
+    if (!is_pow2(N) || !is_pow2(G) || G < 2) return false;
+    const uint32_t LN = ilog2(N);
+    if (LN <= (uint32_t)kMaxLogR || LN > 19) return false;
+    const uint32_t L2 = LN - (LN + 1) / 2;
+    return (1u << L2) >= G * 1u && ((1u << L2) % G) == 0;
+}
+inline PassParams plan_encode_shard(const Buffers& b, size_t N, uint32_t G, uint32_t rank, int which)
+{
+    const uint32_t LN = ilog2(N);
+    const long long q = (long long)(kM / (2 * N));
+    const uint32_t L1 = (LN + 1) / 2, L2 = LN - L1;
+    const uint32_t N1 = 1u << L1, N2 = 1u << L2;
+    const gf::Tw invN = gf::make_tw(gf::inv((uint32_t)N));
+    PassParams p;
+    if (which == 0) {
+        p = base_pass(b, L1);
+        p.nsets = N2 / G;
+        p.src_set_stride = p.dst_set_stride = 1; p.src_row_stride = p.dst_row_stride = N2 / G;
+        p.xf[0] = Xform{emod(-2 * q * (long long)N2), 0, 0};
+        p.prescale = 1; p.pw = invN.w; p.pwhi = invN.whi; p.pwlo = invN.wlo;
+    } else if (which == 1) {
+        p = base_pass(b, L2);
+        p.nsets = N1 / G;
+        p.src_set_stride = p.dst_set_stride = N2; p.src_row_stride = p.dst_row_stride = 1;
+        p.nxf = 2;
+        p.xf[0] = Xform{emod(-2 * q * (long long)N1), emod(-2 * q * (long long)rank), emod(-2 * q * (long long)G)};
+        p.xf[1] = Xform{emod(2 * q * (long long)N1), emod(q * (long long)N1), 0};
+    } else {
+        p = base_pass(b, L1);
+        p.nsets = N2 / G;
+        p.src_set_stride = p.dst_set_stride = 1; p.src_row_stride = p.dst_row_stride = N2 / G;
+        p.xf[0] = Xform{emod(2 * q * (long long)N2), emod(q + 2 * q * (long long)rank), emod(2 * q * (long long)G)};
+        p.canonical_out = 1;
+    }
+    p.src = b.x; p.dst = b.x;
+    return p;
+}
+
 // Per-set stage tables of a pass: [set][xfi][R] entries of 16 bytes; a single shared set when no twist depends on it.
 inline uint32_t table_sets(const PassParams& P)
 {

@@ -61,6 +61,14 @@ int fastecc_b200_rs_encode(uint32_t** data, size_t N, size_t SIZE_words);
 int fastecc_b200_ntt_u32_dev  (uint32_t* d_blocks, size_t N, size_t SIZE_words, size_t pitch_words, int inverse, void* stream);
 int fastecc_b200_rs_encode_dev(uint32_t* d_blocks, size_t N, size_t SIZE_words, size_t pitch_words, void* stream);
 
+/* ---- one transform sharded over several GPUs (one process per GPU; BASELINE config 4) ---------------------------
+ * Global block i = l*n_ranks + rank is local block l (data in, parity out).  An encode is: pass 0 on every rank,
+ * all-to-all of whole blocks, pass 1, all-to-all, pass 2 -- the exchange is the caller's (fastecc_b200/sharded.py does it
+ * with torch.distributed / NCCL); these are the three local passes of RS.cpp:41-63 with the sharded twists.
+ * N = global number of data blocks, 2^11 .. 2^19; d_local holds N/n_ranks rows of pitch_words (16-byte aligned). */
+int fastecc_b200_rs_encode_shard_pass(uint32_t* d_local, size_t N, int n_ranks, int rank, size_t SIZE_words, size_t pitch_words,
+                                      int which, void* stream);
+
 /* Counters for benchmarking: kernels launched by this library since init (all entry points). */
 unsigned long long fastecc_b200_kernel_launches(void);
 
