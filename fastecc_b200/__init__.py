@@ -24,7 +24,7 @@ MAX_LOG_N = 20
 MAX_LOG_N_ENCODE = 19
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfastecc_b200.so")
+LIB_PATH = os.environ.get("FASTECC_B200_LIB", os.path.join(_HERE, "libfastecc_b200.so"))   # override: A/B builds of the same ABI
 _lib = None
 
 

@@ -32,7 +32,7 @@ constexpr uint32_t GEN = 19;                  // generator used by GF_Root (GF(p
 constexpr uint32_t LOG_M = 20;                // largest power-of-two order: P-1 = 2^20 * 4095
 constexpr uint32_t M = 1u << LOG_M;
 
-struct Tw { uint32_t w, whi, wlo, pad; };     // one twiddle: w and floor(w*2^64/P); 16 bytes
+struct Tw { uint32_t w, whi, wlo, wm; };      // one twiddle: w, floor(w*2^64/P), and w*2^32 mod P (Montgomery form); 16 bytes
 
 // `zero` must be a register holding 0 that the compiler cannot constant-fold (see opaque_zero()): it becomes the
 // high half of the 64-bit addend of the second IMAD.HI, which saves ptxas from re-materialising a zero register
@@ -49,6 +49,29 @@ GF_HD uint32_t mul(uint32_t b, uint32_t w, uint32_t whi, uint32_t wlo, uint32_t 
     uint32_t q = (uint32_t)(((uint64_t)b * whi + t) >> 32);
 #endif
     return q * C + b * w;
+}
+
+// The same product through a Montgomery reduction (R = 2^32): wm = w*2^32 mod P.  P^-1 mod 2^32 = 1 + 2^20, so the
+// reduction factor m = lo*(1 + 2^20) is one LEA on the ALU pipe; T - m*P is divisible by 2^32 and
+// (T - m*P)/2^32 = hi(T) - hi(m*P) lies in (-P, P).  IMAD.WIDE + IMAD.HI + 3 ALU instructions: fewer cycles on the
+// integer-multiply pipe than mul() (2 x IMAD.HI + 2 x IMAD), more on the ALU pipe -- the kernels use mul() for one
+// word of a pair and mul_mont() for the other to load both pipes evenly.  Result in [0, P).
+GF_HD uint32_t mul_mont(uint32_t b, uint32_t wm)
+{
+    const uint64_t T = (uint64_t)b * wm;
+    const uint32_t lo = (uint32_t)T, hi = (uint32_t)(T >> 32);
+    const uint32_t m = lo + (lo << 20);
+#if defined(__CUDA_ARCH__)
+    const uint32_t h2 = __umulhi(m, P);
+    uint32_t r;
+    asm("{\n\t.reg .pred q;\n\t.reg .u32 c;\n\tsub.cc.u32 %0, %1, %2;\n\taddc.u32 c, 0, 0;\n\tsetp.eq.u32 q, c, 0;\n\t@q add.u32 %0, %0, 0xFFF00001;\n\t}"
+        : "=r"(r) : "r"(hi), "r"(h2));
+    return r;
+#else
+    const uint32_t h2 = (uint32_t)(((uint64_t)m * P) >> 32);
+    const uint32_t r = hi - h2;
+    return hi < h2 ? r + P : r;
+#endif
 }
 
 GF_HD uint32_t addl(uint32_t a, uint32_t v)
@@ -98,7 +121,7 @@ inline Tw make_tw(uint32_t w)            // {w, floor(w*2^64/P)} by two 64/32 lo
     const uint64_t n1 = (uint64_t)w << 32;
     const uint64_t whi = n1 / P, rem = n1 % P;
     const uint64_t wlo = (rem << 32) / P;
-    Tw t; t.w = w; t.whi = (uint32_t)whi; t.wlo = (uint32_t)wlo; t.pad = 0; return t;
+    Tw t; t.w = w; t.whi = (uint32_t)whi; t.wlo = (uint32_t)wlo; t.wm = (uint32_t)(n1 % P); return t;
 }
 
 } // namespace gf

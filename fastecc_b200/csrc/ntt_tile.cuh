@@ -139,7 +139,11 @@ FECC_HD void bfly2(uint2& a, uint2& b, const uint4& w, uint32_t zero)
 {
     uint32_t v;
     v = gf::mul(b.x, w.x, w.y, w.z, zero); b.x = gf::subl(a.x, v); a.x = gf::addl(a.x, v);
+#if defined(FECC_MIXED_MONT)
+    v = gf::mul_mont(b.y, w.w);            b.y = gf::subl(a.y, v); a.y = gf::addl(a.y, v);
+#else
     v = gf::mul(b.y, w.x, w.y, w.z, zero); b.y = gf::subl(a.y, v); a.y = gf::addl(a.y, v);
+#endif
 }
 // the same with twiddle 1: b only has to be brought into [0,P) (two ALU instructions) for the lazy add/sub
 FECC_HD void bfly2_trivial(uint2& a, uint2& b)
