@@ -14,6 +14,7 @@
 //   * 64-bit stores of the finished rows straight from registers.
 // The kernel is bound by the integer multiply pipe (IMAD.HI on "fmaheavy"), not by HBM: see profiles/.
 #include "ntt_tile.cuh"
+#include "ntt_warp.cuh"
 #include "ntt_pass.h"
 #include "plan.h"
 #include <cstring>
@@ -161,6 +162,118 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(const PassParams 
     }
 }
 
+__device__ __forceinline__ void tma_store_3d(const void* src, const CUtensorMap* map, uint32_t c0, uint32_t c1, uint32_t c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 :: "l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit()        { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all()      { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Warp-private schedule (ntt_warp.cuh): TMA in, eight independent warps, TMA out.  No block barrier in the tile loop:
+// the tile's arrival is an mbarrier wait, and the last warp to finish a tile (shared counter) writes it back with
+// cp.async.bulk.tensor stores and requests the next one.
+template <int LR, int NXF>
+__global__ void __launch_bounds__(kThreads, 2) ntt_pass_warp_kernel(const PassParams Pin, const __grid_constant__ CUtensorMap src_map,
+                                                                    const __grid_constant__ CUtensorMap dst_map)
+{
+    PassParams P = Pin;
+    P.log_r = LR; P.nxf = NXF;
+    extern __shared__ __align__(1024) uint4 smem[];
+    constexpr uint32_t R = 1u << LR;
+    uint4* tile = smem;
+    uint4* tabs = smem + kTileChunks;                     // [2 buffers][NXF][R]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tabs + 2 * NXF * R);
+    uint32_t* done = reinterpret_cast<uint32_t*>(bar + 1);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint32_t zero = gf::opaque_zero();
+    const uint32_t groups = (P.nstrips + P.strips_per_item - 1) / P.strips_per_item;
+    const uint32_t nitems = P.nsets * groups;
+    constexpr uint32_t kWt = 16384u >> LR;                // words per tile row
+    constexpr uint32_t kWb = kWt < 32u ? kWt : 32u;       // words per row of a column block (TMA box inner extent)
+    constexpr uint32_t kColBlocks = kWt / kWb;
+    constexpr uint32_t kRowsBox = R < 256u ? R : 256u;
+    constexpr uint32_t kRowBoxes = R / kRowsBox;
+    constexpr uint32_t kTableBytes = NXF * R * 16u;
+    const WarpPos wp = warp_pos(LR, tid);
+    const WarpAddr wa = warp_addr(LR, wp);
+
+    uint32_t cur_set, cur_strip;
+    if (!tile_decode(P, groups, nitems, 0, cur_set, cur_strip)) return;
+    uint32_t tb = 0, phase = 0;
+
+    auto box_ptr = [&](uint32_t cb, uint32_t rb) { return tile + cb * (R * (kWb / 4)) + rb * (kRowsBox * (kWb / 4)); };
+    auto request = [&](uint32_t set, uint32_t strip, bool with_tables, uint32_t tbuf) {      // one thread
+        fence_proxy_async();
+        mbar_expect_tx(bar, kTileBytes + (with_tables ? kTableBytes : 0u));
+#pragma unroll
+        for (uint32_t cb = 0; cb < kColBlocks; ++cb)
+#pragma unroll
+            for (uint32_t rb = 0; rb < kRowBoxes; ++rb)
+                tma_load_3d(box_ptr(cb, rb), &src_map, bar, strip * kWt + cb * kWb, rb * kRowsBox, set);
+        if (with_tables) bulk_load(tabs + tbuf * NXF * R, P.tables + (size_t)set * P.table_set_stride, kTableBytes, bar);
+    };
+
+    if (tid == 0) { mbar_init(bar, 1); *done = 0; fence_mbar_init(); }
+    __syncthreads();
+    if (tid == 0) request(cur_set, cur_strip, true, tb);
+
+    for (uint32_t t = 0;; ++t) {
+        mbar_wait(bar, phase);
+        const bool active = warp_col_active(P, wp, cur_strip);
+        const uint4* tw0 = tabs + (tb * NXF) * R;
+        const uint4* tw1 = tw0 + R;
+        RoundRegs r;
+        if (active) warp_phase(P, 0, tid, cur_set, wa, tile, tw0, tw1, r, zero);
+        __syncwarp();
+        if (active) warp_phase(P, 1, tid, cur_set, wa, tile, tw0, tw1, r, zero);
+        if (LR > kStages) {
+            if (active) warp_phase(P, 2, tid, cur_set, wa, tile, tw0, tw1, r, zero);
+            __syncwarp();
+            if (active) warp_phase(P, 3, tid, cur_set, wa, tile, tw0, tw1, r, zero);
+            __syncwarp();
+            if (active) warp_phase(P, 4, tid, cur_set, wa, tile, tw0, tw1, r, zero);
+            if (NXF == 2) {
+                if (active) warp_phase(P, 5, tid, cur_set, wa, tile, tw0, tw1, r, zero);
+                __syncwarp();
+                if (active) warp_phase(P, 6, tid, cur_set, wa, tile, tw0, tw1, r, zero);
+                __syncwarp();
+                if (active) warp_phase(P, 7, tid, cur_set, wa, tile, tw0, tw1, r, zero);
+            }
+        }
+        if (active) warp_phase(P, 8, tid, cur_set, wa, tile, tw0, tw1, r, zero);
+        fence_proxy_async();                              // our generic-proxy writes, before the async-proxy (TMA) read
+        __syncwarp();
+
+        uint32_t nxt_set = 0, nxt_strip = 0;
+        const bool has_next = tile_decode(P, groups, nitems, t + 1, nxt_set, nxt_strip);
+        uint32_t is_last = 0;
+        if (lane == 0) { __threadfence_block(); is_last = (atomicAdd(done, 1u) == (uint32_t)(kThreads / 32 - 1)) ? 1u : 0u; }
+        is_last = __shfl_sync(0xffffffffu, is_last, 0);
+        if (is_last) {                                    // every warp has written its columns: this warp does the tile's I/O
+            if (lane == 0) {
+                __threadfence_block();
+                atomicExch(done, 0u);
+                fence_proxy_async();
+#pragma unroll
+                for (uint32_t cb = 0; cb < kColBlocks; ++cb)
+#pragma unroll
+                    for (uint32_t rb = 0; rb < kRowBoxes; ++rb)
+                        tma_store_3d(box_ptr(cb, rb), &dst_map, cur_strip * kWt + cb * kWb, rb * kRowsBox, cur_set);
+                bulk_commit();
+                if (has_next) { bulk_wait_read_all(); request(nxt_set, nxt_strip, nxt_set != cur_set, tb ^ 1u); }
+                else          bulk_wait_all();
+            }
+            __syncwarp();
+        }
+        if (!has_next) break;
+        phase ^= 1u;
+        if (nxt_set != cur_set) tb ^= 1u;
+        cur_set = nxt_set; cur_strip = nxt_strip;
+    }
+}
+
 // One thread per table entry: tables[set][xfi][idx] = g^exponent (entry 0 of every table is unused).
 __global__ void build_tables_kernel(const PassParams P, uint4* out, uint32_t nsets_tab)
 {
@@ -202,22 +315,41 @@ static EncodeTiledFn encode_tiled()
     return fn;
 }
 
-// 3-D view of the source buffer: [word][row within set][set]
-static bool make_tensor_map(const PassParams& P, CUtensorMap* map)
+// 3-D view of a buffer: [word][row within set][set].  warp_layout: column blocks of <= 32 words with the hardware swizzle
+// that ntt_warp.cuh's cell8() assumes (64-byte rows: SWIZZLE_64B, 128-byte rows: SWIZZLE_128B).
+static bool make_tensor_map(const PassParams& P, bool dst, bool warp_layout, CUtensorMap* map)
 {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return false;
     const uint32_t R = 1u << P.log_r, Wt = 16384u >> P.log_r;
-    if (Wt > 256) return false;
+    const uint32_t Wb = warp_layout ? (Wt < 32u ? Wt : 32u) : Wt;
+    if (Wb > 256) return false;
     const cuuint64_t row_bytes = (cuuint64_t)P.pitch4 * 16;
+    const uint32_t rstride = dst ? P.dst_row_stride : P.src_row_stride, sstride = dst ? P.dst_set_stride : P.src_set_stride;
     cuuint64_t gdim[3] = {(cuuint64_t)P.s4 * 4, R, P.nsets};
-    cuuint64_t gstr[2] = {(cuuint64_t)P.src_row_stride * row_bytes, P.nsets > 1 ? (cuuint64_t)P.src_set_stride * row_bytes : (cuuint64_t)P.src_row_stride * row_bytes * R};
-    cuuint32_t box[3] = {Wt, R < 256u ? R : 256u, 1};
+    cuuint64_t gstr[2] = {(cuuint64_t)rstride * row_bytes, P.nsets > 1 ? (cuuint64_t)sstride * row_bytes : (cuuint64_t)rstride * row_bytes * R};
+    cuuint32_t box[3] = {Wb, R < 256u ? R : 256u, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     if (gstr[0] >= (1ull << 40) || gstr[1] >= (1ull << 40)) return false;
-    CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void*)P.src, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUtensorMapSwizzle sw = !warp_layout ? CU_TENSOR_MAP_SWIZZLE_NONE : (Wb * 4 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+    void* base = dst ? (void*)P.dst : (void*)P.src;
+    CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      sw, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return rc == CUDA_SUCCESS;
+}
+
+template <int LR, int NXF>
+static cudaError_t launch_warp_inst(const PassParams& P, const CUtensorMap& smap, const CUtensorMap& dmap, unsigned grid, cudaStream_t stream)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(ntt_pass_warp_kernel<LR, NXF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kTileBytes + 2 * NXF * (16 << LR) + 16);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    ntt_pass_warp_kernel<LR, NXF><<<grid, kThreads, pass_smem_bytes(P), stream>>>(P, smap, dmap);
+    return cudaGetLastError();
 }
 
 template <int LR, int NXF, int TMA>
@@ -248,7 +380,19 @@ cudaError_t launch_pass(const PassParams& Pin, int num_sms, cudaStream_t stream)
     CUtensorMap map;
     memset(&map, 0, sizeof map);
     static const bool no_tma = getenv("FASTECC_B200_NO_TMA") != nullptr;
-    const bool tma = !no_tma && P.log_r >= 6 && make_tensor_map(P, &map);
+    static const bool v8 = getenv("FASTECC_B200_KERNEL") && !strcmp(getenv("FASTECC_B200_KERNEL"), "v8");   // CTA-level schedule (A/B)
+    if (!v8 && !no_tma) {
+        CUtensorMap smap, dmap;
+        if (make_tensor_map(P, false, true, &smap) && make_tensor_map(P, true, true, &dmap)) {
+#define FECC_WCASE(L) case L: return P.nxf == 2 ? launch_warp_inst<L, 2>(P, smap, dmap, g, stream) : launch_warp_inst<L, 1>(P, smap, dmap, g, stream);
+            switch (P.log_r) {
+                FECC_WCASE(5) FECC_WCASE(6) FECC_WCASE(7) FECC_WCASE(8) FECC_WCASE(9) FECC_WCASE(10)
+                default: return cudaErrorInvalidValue;
+            }
+#undef FECC_WCASE
+        }
+    }
+    const bool tma = !no_tma && P.log_r >= 6 && make_tensor_map(P, false, false, &map);
 #define FECC_CASE(L) case L: \
         if (tma) return P.nxf == 2 ? launch_inst<L, 2, 1>(P, map, g, stream) : launch_inst<L, 1, 1>(P, map, g, stream); \
         else     return P.nxf == 2 ? launch_inst<L, 2, 0>(P, map, g, stream) : launch_inst<L, 1, 0>(P, map, g, stream);
