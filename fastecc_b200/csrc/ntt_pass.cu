@@ -171,21 +171,21 @@ __device__ __forceinline__ void bulk_commit()        { asm volatile("cp.async.bu
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all()      { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// Warp-private schedule (ntt_warp.cuh): TMA in, eight independent warps, TMA out.  No block barrier in the tile loop:
-// the tile's arrival is an mbarrier wait, and the last warp to finish a tile (shared counter) writes it back with
-// cp.async.bulk.tensor stores and requests the next one.
+// Warp-private schedule (ntt_warp.cuh): TMA in, eight independent warps, TMA out, one CTA per SM with TWO tile buffers.
+// No block barrier in the tile loop: a tile's arrival is an mbarrier wait; the last warp to finish a tile (shared
+// counter) writes it back with cp.async.bulk.tensor stores and, once the store has read the buffer, requests the tile
+// after next into it -- which then has a whole tile's worth of butterflies to land.
 template <int LR, int NXF>
-__global__ void __launch_bounds__(kThreads, 2) ntt_pass_warp_kernel(const PassParams Pin, const __grid_constant__ CUtensorMap src_map,
+__global__ void __launch_bounds__(kThreads, 1) ntt_pass_warp_kernel(const PassParams Pin, const __grid_constant__ CUtensorMap src_map,
                                                                     const __grid_constant__ CUtensorMap dst_map)
 {
     PassParams P = Pin;
     P.log_r = LR; P.nxf = NXF;
     extern __shared__ __align__(1024) uint4 smem[];
     constexpr uint32_t R = 1u << LR;
-    uint4* tile = smem;
-    uint4* tabs = smem + kTileChunks;                     // [2 buffers][NXF][R]
-    uint64_t* bar = reinterpret_cast<uint64_t*>(tabs + 2 * NXF * R);
-    uint32_t* done = reinterpret_cast<uint32_t*>(bar + 1);
+    uint4* tabs = smem + 2 * kTileChunks;                 // [2 buffers][NXF][R]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tabs + 2 * NXF * R);      // full[2]
+    uint32_t* done = reinterpret_cast<uint32_t*>(bar + 2);                // done[2]
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     const uint32_t zero = gf::opaque_zero();
     const uint32_t groups = (P.nstrips + P.strips_per_item - 1) / P.strips_per_item;
@@ -201,26 +201,34 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_warp_kernel(const PassPa
 
     uint32_t cur_set, cur_strip;
     if (!tile_decode(P, groups, nitems, 0, cur_set, cur_strip)) return;
-    uint32_t tb = 0, phase = 0;
 
-    auto box_ptr = [&](uint32_t cb, uint32_t rb) { return tile + cb * (R * (kWb / 4)) + rb * (kRowsBox * (kWb / 4)); };
-    auto request = [&](uint32_t set, uint32_t strip, bool with_tables, uint32_t tbuf) {      // one thread
+    auto box_ptr = [&](uint32_t buf, uint32_t cb, uint32_t rb) { return smem + buf * kTileChunks + cb * (R * (kWb / 4)) + rb * (kRowsBox * (kWb / 4)); };
+    auto request = [&](uint32_t buf, uint32_t set, uint32_t strip, bool with_tables, uint32_t tbuf) {      // one thread
         fence_proxy_async();
-        mbar_expect_tx(bar, kTileBytes + (with_tables ? kTableBytes : 0u));
+        mbar_expect_tx(bar + buf, kTileBytes + (with_tables ? kTableBytes : 0u));
 #pragma unroll
         for (uint32_t cb = 0; cb < kColBlocks; ++cb)
 #pragma unroll
             for (uint32_t rb = 0; rb < kRowBoxes; ++rb)
-                tma_load_3d(box_ptr(cb, rb), &src_map, bar, strip * kWt + cb * kWb, rb * kRowsBox, set);
-        if (with_tables) bulk_load(tabs + tbuf * NXF * R, P.tables + (size_t)set * P.table_set_stride, kTableBytes, bar);
+                tma_load_3d(box_ptr(buf, cb, rb), &src_map, bar + buf, strip * kWt + cb * kWb, rb * kRowsBox, set);
+        if (with_tables) bulk_load(tabs + tbuf * NXF * R, P.tables + (size_t)set * P.table_set_stride, kTableBytes, bar + buf);
     };
 
-    if (tid == 0) { mbar_init(bar, 1); *done = 0; fence_mbar_init(); }
+    if (tid == 0) {
+        mbar_init(bar, 1); mbar_init(bar + 1, 1); done[0] = 0; done[1] = 0; fence_mbar_init();
+    }
     __syncthreads();
-    if (tid == 0) request(cur_set, cur_strip, true, tb);
+    if (tid == 0) {                                       // prologue: tiles 0 and 1
+        request(0, cur_set, cur_strip, true, 0);
+        uint32_t s1, st1;
+        if (tile_decode(P, groups, nitems, 1, s1, st1)) request(1, s1, st1, s1 != cur_set, 1);
+    }
 
+    uint32_t tb = 0;                                      // table buffer of the current tile (flips at every set change)
     for (uint32_t t = 0;; ++t) {
-        mbar_wait(bar, phase);
+        const uint32_t buf = t & 1u;
+        uint4* tile = smem + buf * kTileChunks;
+        mbar_wait(bar + buf, (t >> 1) & 1u);
         const bool active = warp_col_active(P, wp, cur_strip);
         const uint4* tw0 = tabs + (tb * NXF) * R;
         const uint4* tw1 = tw0 + R;
@@ -246,31 +254,36 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_warp_kernel(const PassPa
         fence_proxy_async();                              // our generic-proxy writes, before the async-proxy (TMA) read
         __syncwarp();
 
-        uint32_t nxt_set = 0, nxt_strip = 0;
-        const bool has_next = tile_decode(P, groups, nitems, t + 1, nxt_set, nxt_strip);
+        uint32_t n1_set = 0, n1_strip = 0;
+        const bool has_n1 = tile_decode(P, groups, nitems, t + 1, n1_set, n1_strip);
         uint32_t is_last = 0;
-        if (lane == 0) { __threadfence_block(); is_last = (atomicAdd(done, 1u) == (uint32_t)(kThreads / 32 - 1)) ? 1u : 0u; }
+        if (lane == 0) { __threadfence_block(); is_last = (atomicAdd(done + buf, 1u) == (uint32_t)(kThreads / 32 - 1)) ? 1u : 0u; }
         is_last = __shfl_sync(0xffffffffu, is_last, 0);
         if (is_last) {                                    // every warp has written its columns: this warp does the tile's I/O
             if (lane == 0) {
                 __threadfence_block();
-                atomicExch(done, 0u);
+                atomicExch(done + buf, 0u);
                 fence_proxy_async();
 #pragma unroll
                 for (uint32_t cb = 0; cb < kColBlocks; ++cb)
 #pragma unroll
                     for (uint32_t rb = 0; rb < kRowBoxes; ++rb)
-                        tma_store_3d(box_ptr(cb, rb), &dst_map, cur_strip * kWt + cb * kWb, rb * kRowsBox, cur_set);
+                        tma_store_3d(box_ptr(buf, cb, rb), &dst_map, cur_strip * kWt + cb * kWb, rb * kRowsBox, cur_set);
                 bulk_commit();
-                if (has_next) { bulk_wait_read_all(); request(nxt_set, nxt_strip, nxt_set != cur_set, tb ^ 1u); }
-                else          bulk_wait_all();
+                uint32_t n2_set = 0, n2_strip = 0;
+                if (has_n1 && tile_decode(P, groups, nitems, t + 2, n2_set, n2_strip)) {
+                    bulk_wait_read_all();                 // the store has read this buffer: refill it with the tile after next
+                    const uint32_t tb1 = tb ^ (n1_set != cur_set ? 1u : 0u);
+                    request(buf, n2_set, n2_strip, n2_set != n1_set, tb1 ^ 1u);
+                } else {
+                    bulk_wait_all();
+                }
             }
             __syncwarp();
         }
-        if (!has_next) break;
-        phase ^= 1u;
-        if (nxt_set != cur_set) tb ^= 1u;
-        cur_set = nxt_set; cur_strip = nxt_strip;
+        if (!has_n1) break;
+        if (n1_set != cur_set) tb ^= 1u;
+        cur_set = n1_set; cur_strip = n1_strip;
     }
 }
 
@@ -344,11 +357,11 @@ static cudaError_t launch_warp_inst(const PassParams& P, const CUtensorMap& smap
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(ntt_pass_warp_kernel<LR, NXF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             kTileBytes + 2 * NXF * (16 << LR) + 16);
+                                             2 * kTileBytes + 2 * NXF * (16 << LR) + 32);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    ntt_pass_warp_kernel<LR, NXF><<<grid, kThreads, pass_smem_bytes(P), stream>>>(P, smap, dmap);
+    ntt_pass_warp_kernel<LR, NXF><<<grid, kThreads, 2 * kTileBytes + 2 * NXF * (16 << LR) + 32, stream>>>(P, smap, dmap);
     return cudaGetLastError();
 }
 
@@ -384,7 +397,8 @@ cudaError_t launch_pass(const PassParams& Pin, int num_sms, cudaStream_t stream)
     if (!v8 && !no_tma) {
         CUtensorMap smap, dmap;
         if (make_tensor_map(P, false, true, &smap) && make_tensor_map(P, true, true, &dmap)) {
-#define FECC_WCASE(L) case L: return P.nxf == 2 ? launch_warp_inst<L, 2>(P, smap, dmap, g, stream) : launch_warp_inst<L, 1>(P, smap, dmap, g, stream);
+            const unsigned gw = (unsigned)((unsigned long long)num_sms < nitems ? (unsigned long long)num_sms : nitems);      // one CTA per SM
+#define FECC_WCASE(L) case L: return P.nxf == 2 ? launch_warp_inst<L, 2>(P, smap, dmap, gw, stream) : launch_warp_inst<L, 1>(P, smap, dmap, gw, stream);
             switch (P.log_r) {
                 FECC_WCASE(5) FECC_WCASE(6) FECC_WCASE(7) FECC_WCASE(8) FECC_WCASE(9) FECC_WCASE(10)
                 default: return cudaErrorInvalidValue;
