@@ -49,6 +49,14 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// L2 prefetch of a tensor box (no shared-memory destination): used to pull a work item's whole column block
+// (strips_per_item strips wide, i.e. >= 256 contiguous bytes per row) into L2 a few tiles before its 64-byte-wide
+// tiles are requested -- the strided passes touch a different DRAM page per row, and 64-byte accesses waste most of
+// each page activation.
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, uint32_t c0, uint32_t c1, uint32_t c2)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" :: "l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -71,7 +79,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarr
 // LR / NXF / TMA are compile-time: the kernel patches them into its copy of the parameters, so every shift, stride
 // and placement branch in ntt_tile.cuh folds to an immediate (keeps the 64 data registers from spilling).
 template <int LR, int NXF, int TMA>
-__global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(const PassParams Pin, const __grid_constant__ CUtensorMap tmap)
+__global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(const PassParams Pin, const __grid_constant__ CUtensorMap tmap,
+                                                               const __grid_constant__ CUtensorMap pf_map)
 {
     PassParams P = Pin;
     P.log_r = LR; P.nxf = NXF; P.use_tma = TMA;
@@ -107,6 +116,14 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(const PassParams 
                     tma_load_3d(tile + b * (kRowsBox * (kWt / 4)), &tmap, bar, strip * kWt, b * kRowsBox, set);
                 if (with_tables)
                     bulk_load(tabs + tbuf * NXF * R, P.tables + (size_t)set * P.table_set_stride, kTableBytes, bar);
+                if (P.l2_prefetch && strip % P.strips_per_item == 0) {                  // first tile of an item: pull the NEXT item into L2
+                    const uint32_t item = set * groups + strip / P.strips_per_item + gridDim.x;
+                    if (item < nitems) {
+                        const uint32_t ps = item / groups, pstrip = (item - ps * groups) * P.strips_per_item;
+#pragma unroll
+                        for (uint32_t b = 0; b < kBoxes; ++b) tma_prefetch_3d(&pf_map, pstrip * kWt, b * kRowsBox, ps);
+                    }
+                }
             }
         } else {
             load_tile_cpasync(P, set, strip, tid, tile);
@@ -177,7 +194,7 @@ __device__ __forceinline__ void bulk_wait_all()      { asm volatile("cp.async.bu
 // after next into it -- which then has a whole tile's worth of butterflies to land.
 template <int LR, int NXF>
 __global__ void __launch_bounds__(kThreads, 1) ntt_pass_warp_kernel(const PassParams Pin, const __grid_constant__ CUtensorMap src_map,
-                                                                    const __grid_constant__ CUtensorMap dst_map)
+                                                                    const __grid_constant__ CUtensorMap dst_map, const __grid_constant__ CUtensorMap pf_map)
 {
     PassParams P = Pin;
     P.log_r = LR; P.nxf = NXF;
@@ -212,6 +229,14 @@ __global__ void __launch_bounds__(kThreads, 1) ntt_pass_warp_kernel(const PassPa
             for (uint32_t rb = 0; rb < kRowBoxes; ++rb)
                 tma_load_3d(box_ptr(buf, cb, rb), &src_map, bar + buf, strip * kWt + cb * kWb, rb * kRowsBox, set);
         if (with_tables) bulk_load(tabs + tbuf * NXF * R, P.tables + (size_t)set * P.table_set_stride, kTableBytes, bar + buf);
+        if (P.l2_prefetch && strip % P.strips_per_item == 0) {                          // first tile of an item: pull the NEXT item into L2
+            const uint32_t item = set * groups + strip / P.strips_per_item + gridDim.x;
+            if (item < nitems) {
+                const uint32_t ps = item / groups, pstrip = (item - ps * groups) * P.strips_per_item;
+#pragma unroll
+                for (uint32_t rb = 0; rb < kRowBoxes; ++rb) tma_prefetch_3d(&pf_map, pstrip * kWt, rb * kRowsBox, ps);
+            }
+        }
     };
 
     if (tid == 0) {
@@ -351,8 +376,26 @@ static bool make_tensor_map(const PassParams& P, bool dst, bool warp_layout, CUt
     return rc == CUDA_SUCCESS;
 }
 
+// [word][row within set][set] view of the source with a box one work item wide (strips_per_item strips), for L2 prefetch
+static bool make_prefetch_map(const PassParams& P, CUtensorMap* map)
+{
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return false;
+    const uint32_t R = 1u << P.log_r, Wt = 16384u >> P.log_r;
+    const uint32_t W = Wt * P.strips_per_item;
+    if (W > 256) return false;
+    const cuuint64_t row_bytes = (cuuint64_t)P.pitch4 * 16;
+    cuuint64_t gdim[3] = {(cuuint64_t)P.s4 * 4, R, P.nsets};
+    cuuint64_t gstr[2] = {(cuuint64_t)P.src_row_stride * row_bytes, P.nsets > 1 ? (cuuint64_t)P.src_set_stride * row_bytes : (cuuint64_t)P.src_row_stride * row_bytes * R};
+    cuuint32_t box[3] = {W, R < 256u ? R : 256u, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (gstr[0] >= (1ull << 40) || gstr[1] >= (1ull << 40)) return false;
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void*)P.src, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int LR, int NXF>
-static cudaError_t launch_warp_inst(const PassParams& P, const CUtensorMap& smap, const CUtensorMap& dmap, unsigned grid, cudaStream_t stream)
+static cudaError_t launch_warp_inst(const PassParams& P, const CUtensorMap& smap, const CUtensorMap& dmap, const CUtensorMap& pmap, unsigned grid, cudaStream_t stream)
 {
     static bool attr_set = false;
     if (!attr_set) {
@@ -361,12 +404,12 @@ static cudaError_t launch_warp_inst(const PassParams& P, const CUtensorMap& smap
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    ntt_pass_warp_kernel<LR, NXF><<<grid, kThreads, 2 * kTileBytes + 2 * NXF * (16 << LR) + 32, stream>>>(P, smap, dmap);
+    ntt_pass_warp_kernel<LR, NXF><<<grid, kThreads, 2 * kTileBytes + 2 * NXF * (16 << LR) + 32, stream>>>(P, smap, dmap, pmap);
     return cudaGetLastError();
 }
 
 template <int LR, int NXF, int TMA>
-static cudaError_t launch_inst(const PassParams& P, const CUtensorMap& map, unsigned grid, cudaStream_t stream)
+static cudaError_t launch_inst(const PassParams& P, const CUtensorMap& map, const CUtensorMap& pmap, unsigned grid, cudaStream_t stream)
 {
     static bool attr_set = false;
     if (!attr_set) {
@@ -375,7 +418,7 @@ static cudaError_t launch_inst(const PassParams& P, const CUtensorMap& map, unsi
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    ntt_pass_kernel<LR, NXF, TMA><<<grid, kThreads, pass_smem_bytes(P), stream>>>(P, map);
+    ntt_pass_kernel<LR, NXF, TMA><<<grid, kThreads, pass_smem_bytes(P), stream>>>(P, map, pmap);
     return cudaGetLastError();
 }
 
@@ -390,15 +433,18 @@ cudaError_t launch_pass(const PassParams& Pin, int num_sms, cudaStream_t stream)
     if (grid == 0) return cudaSuccess;
     const unsigned g = (unsigned)grid;
     if (!P.tables) return cudaErrorInvalidValue;
-    CUtensorMap map;
-    memset(&map, 0, sizeof map);
+    CUtensorMap map, pmap;
+    memset(&map, 0, sizeof map); memset(&pmap, 0, sizeof pmap);
+    static const int pf_env = getenv("FASTECC_B200_L2_PREFETCH") ? atoi(getenv("FASTECC_B200_L2_PREFETCH")) : -1;
+    // default: prefetch for passes whose rows are far apart (strided row sets); contiguous row sets stream well already
+    P.l2_prefetch = (pf_env >= 0 ? pf_env != 0 : P.src_row_stride > 1) && P.strips_per_item > 1 && make_prefetch_map(P, &pmap) ? 1u : 0u;
     static const bool no_tma = getenv("FASTECC_B200_NO_TMA") != nullptr;
-    static const bool v8 = getenv("FASTECC_B200_KERNEL") && !strcmp(getenv("FASTECC_B200_KERNEL"), "v8");   // CTA-level schedule (A/B)
+    static const bool v8 = !(getenv("FASTECC_B200_KERNEL") && !strcmp(getenv("FASTECC_B200_KERNEL"), "warp"));   // default: CTA-level schedule; "warp": ntt_warp.cuh
     if (!v8 && !no_tma) {
         CUtensorMap smap, dmap;
         if (make_tensor_map(P, false, true, &smap) && make_tensor_map(P, true, true, &dmap)) {
             const unsigned gw = (unsigned)((unsigned long long)num_sms < nitems ? (unsigned long long)num_sms : nitems);      // one CTA per SM
-#define FECC_WCASE(L) case L: return P.nxf == 2 ? launch_warp_inst<L, 2>(P, smap, dmap, gw, stream) : launch_warp_inst<L, 1>(P, smap, dmap, gw, stream);
+#define FECC_WCASE(L) case L: return P.nxf == 2 ? launch_warp_inst<L, 2>(P, smap, dmap, pmap, gw, stream) : launch_warp_inst<L, 1>(P, smap, dmap, pmap, gw, stream);
             switch (P.log_r) {
                 FECC_WCASE(5) FECC_WCASE(6) FECC_WCASE(7) FECC_WCASE(8) FECC_WCASE(9) FECC_WCASE(10)
                 default: return cudaErrorInvalidValue;
@@ -408,8 +454,8 @@ cudaError_t launch_pass(const PassParams& Pin, int num_sms, cudaStream_t stream)
     }
     const bool tma = !no_tma && P.log_r >= 6 && make_tensor_map(P, false, false, &map);
 #define FECC_CASE(L) case L: \
-        if (tma) return P.nxf == 2 ? launch_inst<L, 2, 1>(P, map, g, stream) : launch_inst<L, 1, 1>(P, map, g, stream); \
-        else     return P.nxf == 2 ? launch_inst<L, 2, 0>(P, map, g, stream) : launch_inst<L, 1, 0>(P, map, g, stream);
+        if (tma) return P.nxf == 2 ? launch_inst<L, 2, 1>(P, map, pmap, g, stream) : launch_inst<L, 1, 1>(P, map, pmap, g, stream); \
+        else     return P.nxf == 2 ? launch_inst<L, 2, 0>(P, map, pmap, g, stream) : launch_inst<L, 1, 0>(P, map, pmap, g, stream);
     switch (P.log_r) {
         FECC_CASE(5) FECC_CASE(6) FECC_CASE(7) FECC_CASE(8) FECC_CASE(9) FECC_CASE(10)
         default: return cudaErrorInvalidValue;
