@@ -87,8 +87,13 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(const PassParams 
     extern __shared__ __align__(1024) uint4 smem[];
     constexpr uint32_t R = 1u << LR;
     uint4* tile = smem;                                   // 4096 chunks, natural row order
-    uint4* tabs = smem + kTileChunks;                     // [2 buffers][NXF][R]
-    uint64_t* bar = reinterpret_cast<uint64_t*>(tabs + 2 * NXF * R);
+    // stage tables: a transform whose twist does not depend on the row set (t1 == 0) has ONE table, loaded once;
+    // the others are double-buffered per set.  Slot of transform x in buffer b: tabs + (b*NXF + x)*R; set-independent
+    // tables always use b = 0 (so a fused BC tile needs 3 slots, a plain A tile 1).
+    uint4* tabs = smem + kTileChunks;
+    const bool var0 = P.xf[0].t1 != 0, var1 = NXF == 2 && P.xf[1].t1 != 0;
+    const uint32_t nslots = var1 ? 4u : (var0 ? (uint32_t)NXF + 1u : (uint32_t)NXF);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tabs + nslots * R);
     const uint32_t tid  = threadIdx.x;
     const uint32_t zero = gf::opaque_zero();
     const uint32_t groups = (P.nstrips + P.strips_per_item - 1) / P.strips_per_item;
@@ -97,7 +102,6 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(const PassParams 
     constexpr uint32_t kWt = 16384u >> LR;                // words per tile row
     constexpr uint32_t kRowsBox = R < 256u ? R : 256u;    // TMA box: kRowsBox rows x kWt words
     constexpr uint32_t kBoxes = R / kRowsBox;
-    constexpr uint32_t kTableBytes = NXF * R * 16u;
 
     uint32_t cur_set, cur_strip;
     if (!tile_decode(P, groups, nitems, 0, cur_set, cur_strip)) return;
@@ -110,12 +114,16 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(const PassParams 
         if (TMA) {
             if (tid == 0) {
                 fence_proxy_async();                      // order our earlier generic-proxy accesses to the tile before the async-proxy writes
-                mbar_expect_tx(bar, kTileBytes + (with_tables ? kTableBytes : 0u));
+                const bool first = with_tables && tbuf == 2u;         // prologue: also the set-independent tables
+                const uint32_t ld0 = with_tables && (var0 || first), ld1 = NXF == 2 && with_tables && (var1 || first);
+                mbar_expect_tx(bar, kTileBytes + (ld0 + ld1) * (R * 16u));
 #pragma unroll
                 for (uint32_t b = 0; b < kBoxes; ++b)
                     tma_load_3d(tile + b * (kRowsBox * (kWt / 4)), &tmap, bar, strip * kWt, b * kRowsBox, set);
-                if (with_tables)
-                    bulk_load(tabs + tbuf * NXF * R, P.tables + (size_t)set * P.table_set_stride, kTableBytes, bar);
+                const uint4* tsrc = P.tables + (size_t)set * P.table_set_stride;
+                const uint32_t tbv = first ? 0u : tbuf;
+                if (ld0) bulk_load(tabs + ((var0 ? tbv : 0u) * NXF + 0) * R, tsrc, R * 16u, bar);
+                if (ld1) bulk_load(tabs + ((var1 ? tbv : 0u) * NXF + 1) * R, tsrc + R, R * 16u, bar);
                 if (P.l2_prefetch && strip % P.strips_per_item == 0) {                  // first tile of an item: pull the NEXT item into L2
                     const uint32_t item = set * groups + strip / P.strips_per_item + gridDim.x;
                     if (item < nitems) {
@@ -127,7 +135,13 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(const PassParams 
             }
         } else {
             load_tile_cpasync(P, set, strip, tid, tile);
-            if (with_tables) load_tables_cpasync(P, set, tid, tabs + tbuf * NXF * R);
+            if (with_tables) {
+                const bool first = tbuf == 2u;
+                const uint32_t tbv = first ? 0u : tbuf;
+                const uint4* tsrc = P.tables + (size_t)set * P.table_set_stride;
+                if (var0 || first) for (uint32_t i = tid; i < R; i += kThreads) copy16(tabs + ((var0 ? tbv : 0u) * NXF + 0) * R + i, tsrc + i);
+                if (NXF == 2 && (var1 || first)) for (uint32_t i = tid; i < R; i += kThreads) copy16(tabs + ((var1 ? tbv : 0u) * NXF + 1) * R + i, tsrc + R + i);
+            }
         }
     };
 
@@ -135,7 +149,7 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(const PassParams 
         if (tid == 0) { mbar_init(bar, 1); mbar_init(rbar, kThreads / 32); fence_mbar_init(); }
         __syncthreads();
     }
-    request(cur_set, cur_strip, true, tb);                // prologue: first tile + its tables
+    request(cur_set, cur_strip, true, 2u);                // prologue: first tile + all its tables (buffer 0)
 
     for (uint32_t t = 0;; ++t) {
         if (TMA) mbar_wait(bar, phase);
@@ -162,8 +176,9 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(const PassParams 
                     if (tile_decode(P, groups, nitems, t + 1, ns, nst)) request(ns, nst, ns != cur_set, tb ^ 1u);
                 }
             }
-            const uint4* tw0 = tabs + (tb * NXF) * R;
-            if (active) round_math(P, st, tid, cur_set, tw0, tw0 + R, r, zero);
+            const uint4* tw0 = tabs + ((var0 ? tb : 0u) * NXF) * R;
+            const uint4* tw1 = tabs + ((var1 ? tb : 0u) * NXF + 1) * R;
+            if (active) round_math(P, st, tid, cur_set, tw0, tw1, r, zero);
             if (!last) {
                 if (active) round_write_tile(P, st.k, st.xfi == 0, tid, tile, r);
                 __syncthreads();
@@ -260,8 +275,8 @@ __global__ void __launch_bounds__(kThreads, 1) ntt_pass_warp_kernel(const PassPa
         RoundRegs r;
         if (active) warp_phase(P, 0, tid, cur_set, wa, tile, tw0, tw1, r, zero);
         __syncwarp();
-        if (active) warp_phase(P, 1, tid, cur_set, wa, tile, tw0, tw1, r, zero);
-        if (LR > kStages) {
+        if (active && !P.debug_skip_math) warp_phase(P, 1, tid, cur_set, wa, tile, tw0, tw1, r, zero);
+        if (LR > kStages && !P.debug_skip_math) {
             if (active) warp_phase(P, 2, tid, cur_set, wa, tile, tw0, tw1, r, zero);
             __syncwarp();
             if (active) warp_phase(P, 3, tid, cur_set, wa, tile, tw0, tw1, r, zero);
@@ -334,9 +349,13 @@ cudaError_t launch_build_tables(PassParams& P, uint4* out, cudaStream_t stream)
     return cudaGetLastError();
 }
 
+// shared memory of the CTA-level kernel: tile + table slots + two mbarriers.  Table slot of transform x in buffer b is
+// (b*nxf + x); buffer 1 is needed only up to the last set-dependent transform.
 size_t pass_smem_bytes(const PassParams& P)
 {
-    return (size_t)kTileBytes + (size_t)2 * P.nxf * ((size_t)16 << P.log_r) + 16;   // + two mbarriers
+    uint32_t slots = P.nxf;                                            // buffer 0
+    if (P.nxf == 2 && P.xf[1].t1) slots = 4; else if (P.xf[0].t1) slots = P.nxf + 1;
+    return (size_t)kTileBytes + (size_t)slots * ((size_t)16 << P.log_r) + 16;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -415,6 +434,7 @@ static cudaError_t launch_inst(const PassParams& P, const CUtensorMap& map, cons
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(ntt_pass_kernel<LR, NXF, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              kTileBytes + 2 * NXF * (16 << LR) + 16);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ntt_pass_kernel<LR, NXF, TMA>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -437,7 +457,9 @@ cudaError_t launch_pass(const PassParams& Pin, int num_sms, cudaStream_t stream)
     memset(&map, 0, sizeof map); memset(&pmap, 0, sizeof pmap);
     static const int pf_env = getenv("FASTECC_B200_L2_PREFETCH") ? atoi(getenv("FASTECC_B200_L2_PREFETCH")) : -1;
     // default: prefetch for passes whose rows are far apart (strided row sets); contiguous row sets stream well already
-    P.l2_prefetch = (pf_env >= 0 ? pf_env != 0 : P.src_row_stride > 1) && P.strips_per_item > 1 && make_prefetch_map(P, &pmap) ? 1u : 0u;
+    P.l2_prefetch = (pf_env > 0) && P.strips_per_item > 1 && make_prefetch_map(P, &pmap) ? 1u : 0u;      // off by default: measured no gain, 2x DRAM reads
+    static const bool skip_math = getenv("FASTECC_B200_DEBUG_SKIP_MATH") != nullptr;                         // memory-pattern ceiling experiment (wrong results!)
+    P.debug_skip_math = skip_math ? 1u : 0u;
     static const bool no_tma = getenv("FASTECC_B200_NO_TMA") != nullptr;
     static const bool v8 = !(getenv("FASTECC_B200_KERNEL") && !strcmp(getenv("FASTECC_B200_KERNEL"), "warp"));   // default: CTA-level schedule; "warp": ntt_warp.cuh
     if (!v8 && !no_tma) {

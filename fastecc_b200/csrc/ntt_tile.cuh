@@ -77,6 +77,7 @@ struct PassParams {
     uint32_t canonical_out;                  // reduce stored words to [0,P)
     const uint4* tables;                     // per-set stage tables [set][xfi][R], built once per plan (build_tables_kernel)
     uint32_t table_set_stride;               // uint4 entries between consecutive sets' tables (0: every set shares set 0's)
+    uint32_t debug_skip_math;                // experiments only: move the tiles without transforming them
     uint32_t l2_prefetch;                    // 1: request an L2 prefetch of the next work item's column block (set by launch_pass)
     uint32_t use_tma;                        // 1: tile/table loads by TMA (cp.async.bulk[.tensor]) + mbarrier; 0: 16-byte cp.async
 };

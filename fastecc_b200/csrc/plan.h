@@ -23,12 +23,29 @@
 #include <vector>
 #include <stdint.h>
 #include <stddef.h>
+#include <stdlib.h>
+#include <string.h>
 #include "ntt_tile.cuh"
 
 namespace fecc {
 
 inline uint32_t ilog2(size_t n) { uint32_t l = 0; while (((size_t)1 << l) < n) ++l; return l; }
 inline bool     is_pow2(size_t n) { return n && !(n & (n - 1)); }
+// N = N1*N2: log2 of the factor handled by the strided passes (A, D; A').  Strided passes touch a different DRAM page
+// per row, so they want wide rows: a 512-row tile has 128-byte rows (measured memory floor 0.94 ms per pass at the
+// headline size) where a 1024-row tile has 64-byte rows (1.40 ms).  Hence L1 <= 9 whenever N2 = N/N1 still fits a
+// tile (<= 1024): 2^19 = 512 x 1024, with the longer, contiguous-row work in the fused pass.
+// FASTECC_B200_SPLIT=hi|lo overrides (ceil / floor of LN/2) for experiments.
+inline uint32_t split_l1(uint32_t LN)
+{
+    static const char* env = getenv("FASTECC_B200_SPLIT");
+    uint32_t L1 = (LN + 1) / 2;
+    if (env && !strcmp(env, "lo")) L1 = LN / 2;
+    else if (!(env && !strcmp(env, "hi")) && L1 > 9) L1 = 9;
+    if (L1 < (uint32_t)kMinLogR) L1 = kMinLogR;
+    if (LN - L1 > (uint32_t)kMaxLogR) L1 = LN - kMaxLogR;
+    return L1;
+}
 
 struct Buffers { uint32_t* x; uint32_t* y; const uint4* tw; uint32_t pitch_words; uint32_t size_words; };
 
@@ -64,7 +81,7 @@ inline std::vector<PassParams> plan_ntt(const Buffers& b, size_t N, bool inverse
         v.push_back(a);
         return v;
     }
-    const uint32_t L1 = (LN + 1) / 2, L2 = LN - L1;
+    const uint32_t L1 = split_l1(LN), L2 = LN - L1;
     const uint32_t N1 = 1u << L1, N2 = 1u << L2;
     PassParams a = base_pass(b, L1);
     a.src = b.x; a.dst = b.y; a.nsets = (uint32_t)N2;
@@ -101,7 +118,7 @@ inline std::vector<PassParams> plan_encode(const Buffers& b, size_t N)
         v.push_back(a);
         return v;
     }
-    const uint32_t L1 = (LN + 1) / 2, L2 = LN - L1;
+    const uint32_t L1 = split_l1(LN), L2 = LN - L1;
     const uint32_t N1 = 1u << L1, N2 = 1u << L2;
     PassParams a = base_pass(b, L1);
     a.src = b.x; a.dst = b.x; a.nsets = (uint32_t)N2;
@@ -139,14 +156,14 @@ inline bool shard_supported(size_t N, uint32_t G)
     if (!is_pow2(N) || !is_pow2(G) || G < 2) return false;
     const uint32_t LN = ilog2(N);
     if (LN <= (uint32_t)kMaxLogR || LN > 19) return false;
-    const uint32_t L2 = LN - (LN + 1) / 2;
+    const uint32_t L2 = LN - split_l1(LN);
     return (1u << L2) >= G * 1u && ((1u << L2) % G) == 0;
 }
 inline PassParams plan_encode_shard(const Buffers& b, size_t N, uint32_t G, uint32_t rank, int which)
 {
     const uint32_t LN = ilog2(N);
     const long long q = (long long)(kM / (2 * N));
-    const uint32_t L1 = (LN + 1) / 2, L2 = LN - L1;
+    const uint32_t L1 = split_l1(LN), L2 = LN - L1;
     const uint32_t N1 = 1u << L1, N2 = 1u << L2;
     const gf::Tw invN = gf::make_tw(gf::inv((uint32_t)N));
     PassParams p;

@@ -15,7 +15,8 @@ def geometry(N: int, G: int):
     LN = N.bit_length() - 1
     if N != 1 << LN or LN < 11 or LN > 19 or G < 2 or G & (G - 1):
         raise ValueError("sharded encode needs N = 2^11..2^19 and a power-of-two number of ranks")
-    L1 = (LN + 1) // 2
+    L1 = min(9, (LN + 1) // 2)                       # csrc/plan.h split_l1()
+    L1 = max(L1, LN - 10, 5)
     N1, N2 = 1 << L1, 1 << (LN - L1)
     if N2 % G:
         raise ValueError("N2 must be a multiple of the number of ranks")
