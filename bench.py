@@ -58,7 +58,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--mode", default="stripes", choices=["stripes", "sharded"],
+    ap.add_argument("--mode", default="stripes", choices=["stripes", "sharded", "sharded-a2a"],
                     help="multi-GPU: independent stripe per GPU (default, weak scaling) or ONE transform sharded over the GPUs with two NCCL all-to-alls (strong scaling, BASELINE config 4)")
     return ap.parse_args()
 
@@ -222,7 +222,7 @@ def run_b200_arm(args):
 
     N, S = 1 << args.log_n, args.block_bytes // 4
     dev = torch.device("cuda", local)
-    if args.mode == "sharded" and world > 1:
+    if args.mode in ("sharded", "sharded-a2a") and world > 1:
         return run_sharded(args, fe, rank, world, local, dev)
     data = torch.empty((N, S), dtype=torch.int32, device=dev)
     flat = data.view(-1)
@@ -319,14 +319,25 @@ def run_sharded(args, fe, rank, world, local, dev):
     N, S = 1 << args.log_n, args.block_bytes // 4
     rows = N // world
     x = (torch.arange(rows * S, device=dev, dtype=torch.int64) * 2654435761 % P).to(torch.int32).view(rows, S)
-    run_pass = sharded.gpu_pass_runner(N, world, rank)
     nbytes = 2.0 * N * S * 4
+    fused = args.mode == "sharded" and sharded.p2p_supported(N, world)
+    if fused:                                   # exchange fused into the kernels' stores over peer memory
+        enc = sharded.P2PShardedEncoder(N, S)
+        enc.x.copy_(x)
+
+        def step(_):
+            return enc.encode()
+    else:                                       # local passes + two NCCL all-to-alls
+        run_pass = sharded.gpu_pass_runner(N, world, rank)
+
+        def step(t):
+            return sharded.rs_encode_sharded(t, N, world, run_pass)
 
     def sync():
         torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
-        x = sharded.rs_encode_sharded(x, N, world, run_pass)
+        x = step(x)
     sync()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -336,7 +347,7 @@ def run_sharded(args, fe, rank, world, local, dev):
     sync()
     ev0.record()
     for _ in range(args.steps):
-        x = sharded.rs_encode_sharded(x, N, world, run_pass)
+        x = step(x)
     ev1.record()
     torch.cuda.synchronize()
     ms = multirank.max_over_ranks(ev0.elapsed_time(ev1), device=dev)
@@ -352,14 +363,17 @@ def run_sharded(args, fe, rank, world, local, dev):
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": "rs_encode N=2^%d data blocks -> 2^%d parity, %d-byte blocks, ONE transform sharded over %d GPUs" % (args.log_n, args.log_n, args.block_bytes, world),
-                       "bytes_per_step": nbytes, "convention": "2*N*SIZE*4 bytes per encode (RS.cpp:38)", "parallelism": "cyclic blocks, 3 local passes + 2 NCCL all-to-all",
+                       "bytes_per_step": nbytes, "convention": "2*N*SIZE*4 bytes per encode (RS.cpp:38)", "parallelism": ("cyclic blocks, 3 passes; passes A and BC store every output row into its owner's HBM over NVLink (peer-mapped, CUDA IPC), 2 one-word all-reduce barriers"
+                                       if fused else "cyclic blocks, 3 local passes + 2 NCCL all-to-all"),
                        "l2": "local arrays (%.0f MiB per GPU) exceed L2" % (N * S * 4 / world / 2**20)},
             "roofline": {"bound": "nvlink", "achieved": a2a_bytes / (ms / args.steps * 1e-3) / 1e9, "peak": link, "unit": "GB/s",
                          "frac": t_link / (ms / args.steps * 1e-3), "traffic": None,
-                         "note": "all-to-all bytes sent per GPU per encode / step time, against the measured 770 GB/s per-direction peer bandwidth"},
+                         "note": "bytes each GPU sends to its peers per encode (2 exchanges of (G-1)/G of the local array) / step time, against the measured 770 GB/s per-direction peer bandwidth"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(out), flush=True)
+    if fused:
+        enc.close()
     dist.destroy_process_group()
     return 0
 

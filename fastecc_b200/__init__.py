@@ -52,6 +52,12 @@ def lib() -> ctypes.CDLL:
         L.fastecc_b200_ntt_u32_dev.argtypes = [vp, sz, sz, sz, ci, vp]; L.fastecc_b200_ntt_u32_dev.restype = ci
         L.fastecc_b200_rs_encode_dev.argtypes = [vp, sz, sz, sz, vp]; L.fastecc_b200_rs_encode_dev.restype = ci
         L.fastecc_b200_rs_encode_shard_pass.argtypes = [vp, sz, ci, ci, sz, sz, ci, vp]; L.fastecc_b200_rs_encode_shard_pass.restype = ci
+        L.fastecc_b200_rs_encode_shard_pass_p2p.argtypes = [vp, vp, sz, ci, ci, sz, sz, ci, vp]; L.fastecc_b200_rs_encode_shard_pass_p2p.restype = ci
+        L.fastecc_b200_dev_alloc.argtypes = [sz]; L.fastecc_b200_dev_alloc.restype = vp
+        L.fastecc_b200_dev_free.argtypes = [vp]; L.fastecc_b200_dev_free.restype = None
+        L.fastecc_b200_ipc_export.argtypes = [vp, vp]; L.fastecc_b200_ipc_export.restype = ci
+        L.fastecc_b200_ipc_open.argtypes = [vp, ctypes.POINTER(vp)]; L.fastecc_b200_ipc_open.restype = ci
+        L.fastecc_b200_ipc_close.argtypes = [vp]; L.fastecc_b200_ipc_close.restype = ci
         L.fastecc_b200_kernel_launches.argtypes = []; L.fastecc_b200_kernel_launches.restype = ctypes.c_ulonglong
         L.fastecc_b200_host_alloc.argtypes = [sz]; L.fastecc_b200_host_alloc.restype = vp
         L.fastecc_b200_host_free.argtypes = [vp]; L.fastecc_b200_host_free.restype = None

@@ -253,6 +253,65 @@ int fastecc_b200_rs_encode_shard_pass(uint32_t* d_local, size_t N, int n_ranks, 
     return 0;
 }
 
+int fastecc_b200_rs_encode_shard_pass_p2p(const uint32_t* d_src, uint32_t* const* d_peers, size_t N, int n_ranks, int rank, size_t size, size_t pitch,
+                                          int which, void* stream)
+{
+    const char* who = "fastecc_b200_rs_encode_shard_pass_p2p";
+    Context* c = g_ctx;
+    if (!c) return fail(FASTECC_B200_ENOINIT, "%s: call fastecc_b200_init() first", who);
+    if (!d_src || !d_peers || which < 0 || which > 2 || rank < 0 || rank >= n_ranks) return fail(FASTECC_B200_EINVAL, "%s: bad arguments", who);
+    if (!shard_p2p_supported(N, (uint32_t)n_ranks))
+        return fail(FASTECC_B200_EINVAL, "%s: N=%zu cannot be sharded over %d ranks with fused exchange (need 2^11..2^19, ranks <= 8 and <= both tile heights / 32)", who, N, n_ranks);
+    if (size == 0 || pitch < size || pitch % 4 || ((uintptr_t)d_src) % 16) return fail(FASTECC_B200_EINVAL, "%s: needs SIZE >= 1, 16-byte aligned buffers and pitch %% 4 == 0", who);
+    for (int r = 0; r < n_ranks; ++r)
+        if (!d_peers[r] || ((uintptr_t)d_peers[r]) % 16) return fail(FASTECC_B200_EINVAL, "%s: peer buffer %d missing or misaligned", who, r);
+    if ((unsigned long long)(N / n_ranks) * (pitch / 4) >= (1ull << 32)) return fail(FASTECC_B200_EINVAL, "%s: local buffer too large", who);
+    cudaStream_t st = (cudaStream_t)stream;
+    PassParams p = plan_encode_shard_p2p(d_src, d_peers, c->d_tw, (uint32_t)pitch, (uint32_t)size, N, (uint32_t)n_ranks, (uint32_t)rank, which);
+    std::vector<DevBuf>& tabs = c->tables[0x80000000u | (uint32_t)n_ranks << 16 | (uint32_t)rank << 8 | ilog2(N)];
+    if (tabs.empty()) tabs.resize(3);
+    if (!tabs[which].p) {
+        CUDA_TRY(tabs[which].reserve(table_bytes(p)));
+        CUDA_TRY(launch_build_tables(p, (uint4*)tabs[which].p, st)); g_launches++;
+    }
+    p.tables = (const uint4*)tabs[which].p;
+    p.table_set_stride = table_sets(p) > 1 ? (p.nxf << p.log_r) : 0u;
+    CUDA_TRY(launch_pass(p, c->num_sms, st)); g_launches++;
+    return 0;
+}
+
+// Device buffers that can be mapped into the other ranks' address spaces (cudaMalloc + CUDA IPC: torch's caching
+// allocator hands out sub-blocks, which cannot be exported).
+void* fastecc_b200_dev_alloc(size_t bytes)
+{
+    if (!g_ctx) { fail(FASTECC_B200_ENOINIT, "fastecc_b200_dev_alloc: call fastecc_b200_init() first"); return nullptr; }
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); fail(FASTECC_B200_ENOMEM, "fastecc_b200_dev_alloc: cudaMalloc(%zu) failed", bytes); return nullptr; }
+    return p;
+}
+void fastecc_b200_dev_free(void* p) { if (p) cudaFree(p); }
+int fastecc_b200_ipc_export(void* d_ptr, void* handle64)
+{
+    if (!g_ctx) return fail(FASTECC_B200_ENOINIT, "fastecc_b200_ipc_export: call fastecc_b200_init() first");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, d_ptr));
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+int fastecc_b200_ipc_open(const void* handle64, void** d_ptr)
+{
+    if (!g_ctx) return fail(FASTECC_B200_ENOINIT, "fastecc_b200_ipc_open: call fastecc_b200_init() first");
+    cudaIpcMemHandle_t h; memcpy(&h, handle64, 64);
+    CUDA_TRY(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+int fastecc_b200_ipc_close(void* d_ptr)
+{
+    CUDA_TRY(cudaIpcCloseMemHandle(d_ptr));
+    return 0;
+}
+
 int fastecc_b200_ntt_u32(uint32_t** data, size_t N, size_t size, int inverse)
 { return run_host(data, N, size, inverse ? 1 : 0, "fastecc_b200_ntt_u32"); }
 

@@ -80,7 +80,14 @@ struct PassParams {
     uint32_t debug_skip_math;                // experiments only: move the tiles without transforming them
     uint32_t l2_prefetch;                    // 1: request an L2 prefetch of the next work item's column block (set by launch_pass)
     uint32_t use_tma;                        // 1: tile/table loads by TMA (cp.async.bulk[.tensor]) + mbarrier; 0: 16-byte cp.async
+    // One transform sharded over 2^log_g GPUs with the exchange fused into the stores (plan_encode_shard_p2p): output
+    // element e of a set goes to buffer peers[e mod G] (peer-mapped device memory, NVLink), row
+    // dst_row_offset + set*dst_set_stride + (e / G)*dst_row_stride.  log_g = 0: everything goes to dst.
+    uint32_t log_g;
+    uint32_t dst_row_offset;
+    uint32_t* peers[8];
 };
+constexpr uint32_t kMaxPeers = 8;
 
 FECC_HD uint32_t bitrev(uint32_t x, uint32_t bits)
 {
@@ -408,9 +415,19 @@ FECC_HD void round_write_global(const PassParams& P, const Step st, uint32_t tid
     const bool fused_last = (P.nxf == 2) && (num_rounds(P.log_r) == 1);
     const RoundCtx c = fused_last ? make_round(P.log_r, 0, 0) : make_round(P.log_r, st.k, tp.j);
     const uint32_t gcol2 = strip * (8192u >> P.log_r) + tp.q2;
-    const uint32_t row0 = set * P.dst_set_stride + c.jbase * P.dst_row_stride;
-    uint2* g0 = reinterpret_cast<uint2*>(P.dst) + ((size_t)row0 * P.pitch4 * 2 + gcol2);
-    const size_t gstep = (((size_t)P.dst_row_stride * P.pitch4 * 2) << c.lb) * sizeof(uint2);      // bytes between slots
+    // sharded, exchange fused into the stores: this thread's output elements jbase + (i << lb) all have the same residue
+    // mod G (plan.h guarantees lb >= log_g), i.e. one destination GPU per thread, chosen here once per tile
+    uint32_t* base = P.dst;
+    uint32_t jb = c.jbase;
+    if (P.log_g) {
+        const uint32_t m = jb & ((1u << P.log_g) - 1u);
+        base = m == 0 ? P.peers[0] : m == 1 ? P.peers[1] : m == 2 ? P.peers[2] : m == 3 ? P.peers[3]
+             : m == 4 ? P.peers[4] : m == 5 ? P.peers[5] : m == 6 ? P.peers[6] : P.peers[7];
+        jb >>= P.log_g;
+    }
+    const uint32_t row0 = P.dst_row_offset + set * P.dst_set_stride + jb * P.dst_row_stride;
+    uint2* g0 = reinterpret_cast<uint2*>(base) + ((size_t)row0 * P.pitch4 * 2 + gcol2);
+    const size_t gstep = ((((size_t)P.dst_row_stride * P.pitch4 * 2) << c.lb) >> P.log_g) * sizeof(uint2);      // bytes between slots
     uint2* gp[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) { gp[u] = g0; opaque_advance(gp[u], gstep * u); }

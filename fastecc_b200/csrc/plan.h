@@ -191,6 +191,34 @@ inline PassParams plan_encode_shard(const Buffers& b, size_t N, uint32_t G, uint
     return p;
 }
 
+// The same three passes with the exchange fused into the stores of passes A and BC: every rank holds two buffers of N/G
+// rows (X: data in / parity out, Y: intermediate), mapped into every other rank (CUDA IPC, NVLink).  Pass A reads the
+// local X and scatters its output rows straight into the Y of their owners (element k1 -> rank k1 mod G, row
+// (k1 / G)*N2 + n2'*G + rank), pass BC reads the local Y and scatters into the owners' X (element j2 -> rank j2 mod G,
+// row (k1'*G + rank)*(N2/G) + j2 / G), pass D is local and in place.  No all-to-all, no staging copies: the transfer
+// is the store traffic of the kernel itself.  Needs every thread's 32 output elements on one rank: G <= 2^(LR-5) for
+// both tile heights.
+inline bool shard_p2p_supported(size_t N, uint32_t G)
+{
+    if (!shard_supported(N, G) || G > kMaxPeers) return false;
+    const uint32_t LN = ilog2(N), L1 = split_l1(LN), L2 = LN - L1, lg = ilog2(G);
+    return L1 >= 5 + lg && L2 >= 5 + lg;
+}
+inline PassParams plan_encode_shard_p2p(const uint32_t* src, uint32_t* const* peers, const uint4* tw, uint32_t pitch_words, uint32_t size_words,
+                                        size_t N, uint32_t G, uint32_t rank, int which)
+{
+    Buffers b{const_cast<uint32_t*>(src), nullptr, tw, pitch_words, size_words};
+    PassParams p = plan_encode_shard(b, N, G, rank, which);
+    if (which == 2) return p;                                       // local, in place
+    const uint32_t LN = ilog2(N), L1 = split_l1(LN), N2 = 1u << (LN - L1);
+    p.log_g = ilog2(G);
+    for (uint32_t r = 0; r < kMaxPeers; ++r) p.peers[r] = peers[r < G ? r : 0];
+    p.dst = peers[rank];
+    if (which == 0) { p.dst_row_stride = N2; p.dst_set_stride = G;  p.dst_row_offset = rank; }
+    else            { p.dst_row_stride = 1;  p.dst_set_stride = N2; p.dst_row_offset = rank * (N2 / G); }
+    return p;
+}
+
 // Per-set stage tables of a pass: [set][xfi][R] entries of 16 bytes; a single shared set when no twist depends on it.
 inline uint32_t table_sets(const PassParams& P)
 {

@@ -1,4 +1,11 @@
-"""One Reed-Solomon encode sharded over G GPUs (BASELINE config 4): local passes + two all-to-alls of whole blocks.
+"""One Reed-Solomon encode sharded over G GPUs (BASELINE config 4).
+
+Two implementations of the same decomposition:
+  * P2PShardedEncoder -- the exchange is FUSED into the pass kernels: passes A and BC store every output row straight
+    into the memory of the GPU that owns it (CUDA IPC mappings, NVLink), so there is no all-to-all, no pack/unpack
+    and no extra trip through HBM; the passes are separated by a one-word NCCL all-reduce (a stream-ordered barrier).
+  * rs_encode_sharded -- local passes + two NCCL all-to-alls of whole blocks (the plain-library baseline; also what the
+    CPU/gloo tests run, with the kernel emulated).
 
 Blocks are dealt cyclically (global block i = l*G + rank is local block l) for the data going in and the parity
 coming out.  N = N1*N2 as in csrc/plan.h; with N2 % G == 0 the row sets of pass A (fixed n2) and pass D (fixed j2)
@@ -74,3 +81,98 @@ def gpu_pass_runner(N: int, G: int, rank: int):
                                                         torch.cuda.current_stream(t.device).cuda_stream)
         fe._check(rc)
     return run
+
+
+def p2p_supported(N: int, G: int) -> bool:
+    """csrc/plan.h shard_p2p_supported(): <= 8 ranks and every thread's 32 output rows on one rank for both tile heights."""
+    try:
+        N1, N2 = geometry(N, G)
+    except ValueError:
+        return False
+    lg = G.bit_length() - 1
+    return G <= 8 and N1.bit_length() - 1 >= 5 + lg and N2.bit_length() - 1 >= 5 + lg
+
+
+class _RawCudaBuffer:
+    """A cudaMalloc'ed block exposed through __cuda_array_interface__ (torch.as_tensor keeps this object alive)."""
+    def __init__(self, ptr: int, shape, typestr="<i4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class P2PShardedEncoder:
+    """ONE encode of N blocks of S words over the G ranks of `group`, exchange fused into the kernels' stores.
+
+    enc.x is this rank's [N/G, S] int32 CUDA tensor: fill it with the local data blocks (global block l*G + rank is row l),
+    call enc.encode(), read the local parity blocks from the same tensor.  Collective: every rank constructs it and calls
+    encode() the same number of times.  One process per GPU on one node (CUDA IPC)."""
+
+    def __init__(self, N: int, S: int, group=None):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        import fastecc_b200 as fe
+        self.N, self.S, self.group = N, S, group
+        self.G, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if not p2p_supported(N, self.G) or S % 4:
+            raise ValueError("fused-exchange sharding needs N = 2^15..2^19 (fewer ranks: from 2^12), <= 8 ranks, SIZE % 4 == 0")
+        self._lib = L = fe.lib()
+        self._dev = torch.cuda.current_device()
+        fe.init(self._dev)
+        rows = N // self.G
+        nbytes = rows * S * 4
+        self._own = [L.fastecc_b200_dev_alloc(nbytes), L.fastecc_b200_dev_alloc(nbytes)]          # X, Y
+        if not all(self._own):
+            raise MemoryError(L.fastecc_b200_last_error().decode())
+        handles = torch.empty(128, dtype=torch.uint8)
+        hb = (ctypes.c_ubyte * 128)()
+        for k in range(2):
+            fe._check(L.fastecc_b200_ipc_export(self._own[k], ctypes.addressof(hb) + 64 * k))
+        handles.copy_(torch.frombuffer(bytearray(hb), dtype=torch.uint8))
+        dev_handles = handles.cuda()
+        everyone = torch.empty(128 * self.G, dtype=torch.uint8, device=dev_handles.device)
+        dist.all_gather_into_tensor(everyone, dev_handles, group=group)
+        everyone = everyone.cpu().numpy().reshape(self.G, 2, 64)
+        self._opened = []
+        peers = [[0] * self.G, [0] * self.G]
+        for r in range(self.G):
+            for k in range(2):
+                if r == self.rank:
+                    peers[k][r] = self._own[k]
+                else:
+                    p = ctypes.c_void_p()
+                    fe._check(L.fastecc_b200_ipc_open(everyone[r, k].ctypes.data, ctypes.byref(p)))
+                    peers[k][r] = p.value
+                    self._opened.append(p.value)
+        self._xp = (ctypes.c_void_p * self.G)(*peers[0])
+        self._yp = (ctypes.c_void_p * self.G)(*peers[1])
+        self.x = torch.as_tensor(_RawCudaBuffer(self._own[0], (rows, S)), device=torch.device("cuda", self._dev))
+        self._flag = torch.zeros(1, dtype=torch.int32, device=self.x.device)
+        self._barrier()                                                # nobody stores into a peer before everybody has mapped everything
+
+    def _barrier(self):
+        import torch.distributed as dist
+        dist.all_reduce(self._flag, group=self.group)                  # on the current stream: orders the passes of all ranks
+
+    def encode(self):
+        import torch
+        import fastecc_b200 as fe
+        L, st = self._lib, torch.cuda.current_stream().cuda_stream
+        X, Y = self._own
+        fe._check(L.fastecc_b200_rs_encode_shard_pass_p2p(X, self._yp, self.N, self.G, self.rank, self.S, self.S, 0, st))
+        self._barrier()
+        fe._check(L.fastecc_b200_rs_encode_shard_pass_p2p(Y, self._xp, self.N, self.G, self.rank, self.S, self.S, 1, st))
+        self._barrier()
+        fe._check(L.fastecc_b200_rs_encode_shard_pass_p2p(X, self._xp, self.N, self.G, self.rank, self.S, self.S, 2, st))
+        return self.x
+
+    def close(self):
+        import torch
+        if self._own:
+            torch.cuda.synchronize()
+            self._barrier(); torch.cuda.synchronize()                  # no peer is still storing into our buffers
+            for p in self._opened:
+                self._lib.fastecc_b200_ipc_close(p)
+            self.x = None
+            for p in self._own:
+                self._lib.fastecc_b200_dev_free(p)
+            self._own, self._opened = [], []

@@ -69,6 +69,22 @@ int fastecc_b200_rs_encode_dev(uint32_t* d_blocks, size_t N, size_t SIZE_words, 
 int fastecc_b200_rs_encode_shard_pass(uint32_t* d_local, size_t N, int n_ranks, int rank, size_t SIZE_words, size_t pitch_words,
                                       int which, void* stream);
 
+/* The same passes with the exchange FUSED into the kernels' stores (no all-to-all, no staging): every rank owns two
+ * buffers of N/n_ranks rows, X (data in / parity out) and Y (intermediate), allocated with fastecc_b200_dev_alloc and
+ * mapped into the other ranks with fastecc_b200_ipc_export / _open (CUDA IPC; peer access over NVLink).
+ *   which 0: reads the local X, writes the rows of Y on their owners     d_src = X_local, d_peers[r] = rank r's Y
+ *   which 1: reads the local Y, writes the rows of X on their owners     d_src = Y_local, d_peers[r] = rank r's X
+ *   which 2: local, in place on X                                        d_src = X_local, d_peers[rank] = X_local
+ * d_peers: HOST array of n_ranks device pointers (own buffer at [rank]).  The caller separates the passes with a
+ * cross-rank barrier on the stream (fastecc_b200/sharded.py: a one-word NCCL all-reduce).  n_ranks <= 8, N = 2^15..2^19. */
+int fastecc_b200_rs_encode_shard_pass_p2p(const uint32_t* d_src, uint32_t* const* d_peers, size_t N, int n_ranks, int rank,
+                                          size_t SIZE_words, size_t pitch_words, int which, void* stream);
+void* fastecc_b200_dev_alloc(size_t bytes);                       /* cudaMalloc: exportable, unlike a caching-allocator block */
+void  fastecc_b200_dev_free(void* d_ptr);
+int   fastecc_b200_ipc_export(void* d_ptr, void* handle64);       /* 64-byte cudaIpcMemHandle_t */
+int   fastecc_b200_ipc_open(const void* handle64, void** d_ptr);  /* in another process on the same node */
+int   fastecc_b200_ipc_close(void* d_ptr);
+
 /* Counters for benchmarking: kernels launched by this library since init (all entry points). */
 unsigned long long fastecc_b200_kernel_launches(void);
 

@@ -17,6 +17,13 @@ extern "C" int emu_rs_encode_shard_pass(uint32_t* x, size_t N, int n_ranks, int 
     emulate_pass(plan_encode_shard(b, N, (uint32_t)n_ranks, (uint32_t)rank, which));
     return 0;
 }
+extern "C" int emu_rs_encode_shard_pass_p2p(const uint32_t* src, uint32_t* const* peers, size_t N, int n_ranks, int rank, size_t size, size_t pitch, int which)
+{
+    if (!shard_p2p_supported(N, (uint32_t)n_ranks) || pitch % 4 || which < 0 || which > 2) return -1;
+    emulate_pass(plan_encode_shard_p2p(src, peers, reinterpret_cast<const uint4*>(power_table().data()), (uint32_t)pitch, (uint32_t)size,
+                                       N, (uint32_t)n_ranks, (uint32_t)rank, which));
+    return 0;
+}
 extern "C" int emu_rs_encode(uint32_t* x, size_t N, size_t size, size_t pitch)
 {
     Buffers b{x, nullptr, reinterpret_cast<const uint4*>(power_table().data()), (uint32_t)pitch, (uint32_t)size};

@@ -199,6 +199,30 @@ def test_full_size_encode_linearity(fecc, oracle):
     assert ok
 
 
+@pytest.mark.parametrize("L,S", [(11, 16384), (12, 8192), (13, 4096), (14, 2048), (15, 1024), (16, 512), (17, 256), (18, 128), (19, 64), (20, 32)])
+def test_many_tiles_column_sample(fecc, oracle, L, S):
+    """128 MiB of blocks at every two-pass order: enough tiles per SM for the dual (two groups, three tile buffers)
+    schedule of the single-transform passes.  The transform is independent per word column, so a sample of columns of
+    the device result is compared with the oracle run on just those columns."""
+    import torch
+    N = 1 << L
+    rng = np.random.default_rng(1000 + L)
+    a = rng.integers(0, P, size=(N, S), dtype=np.uint64).astype(np.uint32)
+    cols = np.r_[0:8, S // 2 - 4:S // 2 + 4, S - 8:S]
+    sub = np.ascontiguousarray(a[:, cols])
+    ops = [("ntt", False), ("intt", True)] + ([("encode", None)] if L <= 19 else [])
+    for name, inv in ops:
+        t = to_dev(a)
+        if name == "encode":
+            fecc.rs_encode_dev(t); want = ol.o_encode(oracle, sub)
+        else:
+            fecc.ntt_dev(t, inv); want = ol.o_ntt(oracle, sub, inv)
+        got = to_host(t[:, torch.from_numpy(cols).cuda()].contiguous())
+        assert np.array_equal(got, want), name
+        del t
+    torch.cuda.empty_cache()
+
+
 def test_argument_validation(fecc):
     a = np.zeros((3, 4), dtype=np.uint32)
     with pytest.raises(fecc.FastEccError) as e:

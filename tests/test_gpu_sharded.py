@@ -1,5 +1,5 @@
-"""Multi-GPU (>= 2 visible B200s): ONE encode sharded over the GPUs with NCCL all-to-alls must equal the single-GPU /
-oracle result bit for bit.  Skipped on a single-GPU box (the CPU gloo test covers the logic there)."""
+"""Multi-GPU (>= 2 visible B200s): ONE encode sharded over the GPUs -- with the exchange fused into the kernels' stores
+over peer memory (P2PShardedEncoder) and with NCCL all-to-alls (rs_encode_sharded) -- must equal the oracle bit for bit.  Skipped on a single-GPU box (the CPU gloo test covers the logic there)."""
 import os
 import socket
 import sys
@@ -15,6 +15,37 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker_p2p(rank, world, port, L, S, q):
+    import torch
+    import torch.distributed as dist
+    import oracle_lib as ol
+    import fastecc_b200 as fe
+    from fastecc_b200 import sharded
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    fe.init(rank)
+    N = 1 << L
+    o = ol.load_oracle()
+    full = ol.fill_B(o, N, S)
+    enc = sharded.P2PShardedEncoder(N, S)
+    ok = True
+    for rep in range(2):                                                   # twice: buffers and barriers are reused
+        enc.x.copy_(torch.from_numpy(np.ascontiguousarray(full[rank::world]).view(np.int32)))
+        out = enc.encode().clone()
+        gathered = [torch.empty_like(out) for _ in range(world)] if rank == 0 else None
+        dist.gather(out, gathered, dst=0)
+        if rank == 0:
+            par = np.empty((N, S), dtype=np.uint32)
+            for r in range(world):
+                par[r::world] = gathered[r].cpu().numpy().view(np.uint32)
+            ok = ok and bool(np.array_equal(par, ol.o_encode(o, full)))
+    enc.close()
+    if rank == 0:
+        q.put(ok)
+    dist.destroy_process_group()
 
 
 def _worker(rank, world, port, L, S, q):
@@ -40,6 +71,31 @@ def _worker(rank, world, port, L, S, q):
             par[r::world] = gathered[r].cpu().numpy().view(np.uint32)
         q.put(bool(np.array_equal(par, ol.o_encode(o, full))))
     dist.destroy_process_group()
+
+
+def _run(worker, L, S):
+    import torch
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 1 << (world.bit_length() - 1)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=worker, args=(r, world, port, L, S, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert ok
+
+
+@pytest.mark.parametrize("L,S", [(16, 64), (17, 1024)])
+def test_p2p_fused_exchange_encode_on_gpus(L, S):
+    _run(_worker_p2p, L, S)
 
 
 @pytest.mark.parametrize("L,S", [(11, 64), (16, 1024)])
