@@ -216,6 +216,7 @@ def run_b200_arm(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep NCCL's banner off stdout: rank 0 prints exactly one JSON line there
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import fastecc_b200 as fe
     fe.init(local)                      # raises if the CUDA library or an sm_100 GPU is missing: no fallback
