@@ -127,7 +127,23 @@ def load_ref_lib():
     r.ref_rs_encode.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t]
     r.ref_num_threads.restype = ctypes.c_int
     r.ref_build_flavour.restype = ctypes.c_char_p
+    if hasattr(r, "ref_set_num_threads"):
+        r.ref_set_num_threads.argtypes = [ctypes.c_int]; r.ref_set_num_threads.restype = None
     return r
+
+
+def host_thread_candidates():
+    """Thread counts worth trying for the CPU reference: one per physical core and one per hardware thread of this
+    process's affinity mask (the reference blocks for the caches of a core: SMT siblings can hurt it, 1.8 s vs 4.6 s
+    per encode on a 64-core / 128-thread host)."""
+    cpus = sorted(os.sched_getaffinity(0))
+    cores = set()
+    for c in cpus:
+        try:
+            cores.add(open("/sys/devices/system/cpu/cpu%d/topology/thread_siblings_list" % c).read().strip())
+        except OSError:
+            cores.add(str(c))
+    return sorted({max(1, len(cores)), len(cpus)})
 
 
 def load_oracle_port():
@@ -136,7 +152,7 @@ def load_oracle_port():
     return oracle_lib.load_oracle()
 
 
-def cpu_encode_runner(log_n, size_words):
+def cpu_encode_runner(log_n, size_words, calibrate=True):
     """Returns (fn, kind, cores, label): fn() runs one full CPU encode of 2^log_n x size_words in place."""
     import numpy as np
     N = 1 << log_n
@@ -145,8 +161,22 @@ def cpu_encode_runner(log_n, size_words):
     if r is not None:
         # T** data, RS.cpp:31-33; left permuted between steps like the reference leaves it
         tab = buf.ctypes.data + np.arange(N, dtype=np.uint64) * np.uint64(size_words * 4)
-        return (lambda _keep=buf: r.ref_rs_encode(tab.ctypes.data, N, size_words)), "reference", int(r.ref_num_threads()), \
-            "unmodified FastECC templates, %s+OpenMP build (oracle/_ref)" % r.ref_build_flavour().decode()
+        fn = lambda _keep=buf: r.ref_rs_encode(tab.ctypes.data, N, size_words)      # noqa: E731
+        note = ""
+        cands = host_thread_candidates()
+        if hasattr(r, "ref_set_num_threads") and calibrate:
+            best = None
+            for n in cands:                                   # give the reference its best thread count on this host
+                r.ref_set_num_threads(n)
+                if best is None:
+                    fn()                                      # first touch / page faults are not part of the comparison
+                t0 = time.perf_counter(); fn(); dt = time.perf_counter() - t0
+                if best is None or dt < best[1]:
+                    best = (n, dt)
+            r.ref_set_num_threads(best[0])
+            note = "; thread count picked from %s by one timed encode each" % cands
+        return fn, "reference", int(r.ref_num_threads()), \
+            "unmodified FastECC templates, %s+OpenMP build (oracle/_ref)%s" % (r.ref_build_flavour().decode(), note)
     o = load_oracle_port()
     return (lambda: o.oracle_rs_encode(buf.ctypes.data, N, size_words)), "port", int(o.oracle_num_threads()), "oracle/gfp_oracle.c (plain C port, OpenMP)"
 
@@ -156,7 +186,7 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     os.environ.setdefault("OMP_WAIT_POLICY", "active")
-    os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))      # torchrun pins it to 1: the reference gets every host thread
+    os.environ["OMP_NUM_THREADS"] = str(host_thread_candidates()[0])       # torchrun pins it to 1; cpu_encode_runner() then picks the better of cores / hardware threads
     size_words = args.block_bytes // 4
     N = 1 << args.log_n
     fn, kind, cores, label = cpu_encode_runner(args.log_n, size_words)
@@ -189,7 +219,7 @@ def quick_cpu_baseline(args):
     """Bounded CPU sample for the own arm's cpu_baseline block: a few full encodes (about 10-30 s of CPU work at most)."""
     try:
         os.environ.setdefault("OMP_WAIT_POLICY", "active")
-        os.environ.setdefault("OMP_NUM_THREADS", str(len(os.sched_getaffinity(0))))
+        os.environ["OMP_NUM_THREADS"] = str(host_thread_candidates()[0])
         size_words = args.block_bytes // 4
         fn, kind, cores, label = cpu_encode_runner(args.log_n, size_words)
         fn()
@@ -355,6 +385,13 @@ def run_sharded(args, fe, rank, world, local, dev):
     launches = fe.kernel_launches() - launches0
     clocks = sampler.stop() if sampler else None
     sync()
+    phases = None
+    if fused:                                   # one more encode with events between the phases (rank 0's view)
+        evs = []
+        enc.encode(events=evs)
+        torch.cuda.synchronize()
+        phases = dict(zip(["pass_A", "barrier_1", "pass_BC", "barrier_2", "pass_D"], [round(evs[i].elapsed_time(evs[i + 1]), 4) for i in range(5)]))
+        sync()
     if rank == 0:
         a2a_bytes = 2.0 * (world - 1) / world * (N * S * 4 / world)           # sent per GPU per encode (two all-to-alls)
         link = 770.0                                                          # GB/s per direction per GPU, measured peer copy (B200_PROFILING.md)
@@ -372,6 +409,8 @@ def run_sharded(args, fe, rank, world, local, dev):
                          "note": "bytes each GPU sends to its peers per encode (2 exchanges of (G-1)/G of the local array) / step time, against the measured 770 GB/s per-direction peer bandwidth"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        if phases:
+            out["phases_ms_rank0"] = phases
         print(json.dumps(out), flush=True)
     if fused:
         enc.close()

@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(const PassParams 
                                                                const __grid_constant__ CUtensorMap pf_map)
 {
     PassParams P = Pin;
-    P.log_r = LR; P.nxf = NXF; P.use_tma = TMA;
+    P.log_r = LR; P.nxf = NXF; P.use_tma = TMA != 0;
+    if (TMA != 2) P.log_g = 0;                            // TMA == 2: the instantiation whose stores pick a destination GPU (sharded, §8)
     extern __shared__ __align__(1024) uint4 smem[];
     constexpr uint32_t R = 1u << LR;
     uint4* tile = smem;                                   // 4096 chunks, natural row order
@@ -206,11 +207,12 @@ __device__ __forceinline__ void group_sync(uint32_t g) { asm volatile("bar.sync 
 // (0.85 ms copy-only) and butterflies (~0.9 ms), so hiding one behind the other is what they need.
 // Stage tables: a set-independent table is loaded once; otherwise each group double-buffers its own (slot 2g + parity),
 // requested one tile ahead by the group itself.
-template <int LR>
+template <int LR, int SHARD>
 __global__ void __launch_bounds__(2 * kThreads, 1) ntt_pass_dual_kernel(const PassParams Pin, const __grid_constant__ CUtensorMap tmap)
 {
     PassParams P = Pin;
     P.log_r = LR; P.nxf = 1; P.use_tma = 1;
+    if (!SHARD) P.log_g = 0;
     extern __shared__ __align__(1024) uint4 smem[];
     constexpr uint32_t R = 1u << LR;
     constexpr uint32_t kBufs = 3;
@@ -540,16 +542,16 @@ static size_t dual_smem_bytes(const PassParams& P)
 {
     return (size_t)3 * kTileBytes + (size_t)(P.xf[0].t1 ? 4 : 1) * ((size_t)16 << P.log_r) + 10 * sizeof(uint64_t);
 }
-template <int LR>
+template <int LR, int SHARD>
 static cudaError_t launch_dual_inst(const PassParams& P, const CUtensorMap& map, unsigned grid, cudaStream_t stream)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(ntt_pass_dual_kernel<LR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        cudaError_t e = cudaFuncSetAttribute(ntt_pass_dual_kernel<LR, SHARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    ntt_pass_dual_kernel<LR><<<grid, 2 * kThreads, dual_smem_bytes(P), stream>>>(P, map);
+    ntt_pass_dual_kernel<LR, SHARD><<<grid, 2 * kThreads, dual_smem_bytes(P), stream>>>(P, map);
     return cudaGetLastError();
 }
 
@@ -601,20 +603,22 @@ cudaError_t launch_pass(const PassParams& Pin, int num_sms, cudaStream_t stream)
         }
     }
     const bool tma = !no_tma && P.log_r >= 6 && make_tensor_map(P, false, false, &map);
+    if (P.log_g && !tma) return cudaErrorNotSupported;          // sharded stores exist only in the TMA instantiations
     // single-transform passes with enough tiles to keep both groups of every SM busy: the dual schedule (3 tile buffers / SM)
     static const bool no_dual = getenv("FASTECC_B200_KERNEL") && !strcmp(getenv("FASTECC_B200_KERNEL"), "cta");
     if (tma && !no_dual && P.nxf == 1 && dual_smem_bytes(P) <= 232448 && nitems * P.strips_per_item >= 4ull * num_sms) {
         const unsigned gd = (unsigned)((unsigned long long)num_sms < nitems ? (unsigned long long)num_sms : nitems);
         switch (P.log_r) {
-            case 6: return launch_dual_inst<6>(P, map, gd, stream);
-            case 7: return launch_dual_inst<7>(P, map, gd, stream);
-            case 8: return launch_dual_inst<8>(P, map, gd, stream);
-            case 9: return launch_dual_inst<9>(P, map, gd, stream);
-            case 10: return launch_dual_inst<10>(P, map, gd, stream);
+            case 6: return P.log_g ? launch_dual_inst<6, 1>(P, map, gd, stream) : launch_dual_inst<6, 0>(P, map, gd, stream);
+            case 7: return P.log_g ? launch_dual_inst<7, 1>(P, map, gd, stream) : launch_dual_inst<7, 0>(P, map, gd, stream);
+            case 8: return P.log_g ? launch_dual_inst<8, 1>(P, map, gd, stream) : launch_dual_inst<8, 0>(P, map, gd, stream);
+            case 9: return P.log_g ? launch_dual_inst<9, 1>(P, map, gd, stream) : launch_dual_inst<9, 0>(P, map, gd, stream);
+            case 10: return P.log_g ? launch_dual_inst<10, 1>(P, map, gd, stream) : launch_dual_inst<10, 0>(P, map, gd, stream);
             default: break;
         }
     }
 #define FECC_CASE(L) case L: \
+        if (tma && P.log_g) return P.nxf == 2 ? launch_inst<L, 2, 2>(P, map, pmap, g, stream) : launch_inst<L, 1, 2>(P, map, pmap, g, stream); \
         if (tma) return P.nxf == 2 ? launch_inst<L, 2, 1>(P, map, pmap, g, stream) : launch_inst<L, 1, 1>(P, map, pmap, g, stream); \
         else     return P.nxf == 2 ? launch_inst<L, 2, 0>(P, map, pmap, g, stream) : launch_inst<L, 1, 0>(P, map, pmap, g, stream);
     switch (P.log_r) {

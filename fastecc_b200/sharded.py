@@ -153,16 +153,27 @@ class P2PShardedEncoder:
         import torch.distributed as dist
         dist.all_reduce(self._flag, group=self.group)                  # on the current stream: orders the passes of all ranks
 
-    def encode(self):
+    def encode(self, events=None):
+        """events: optional list that receives 6 CUDA events bracketing pass A, barrier, pass BC, barrier, pass D."""
         import torch
         import fastecc_b200 as fe
         L, st = self._lib, torch.cuda.current_stream().cuda_stream
         X, Y = self._own
+
+        def mark():
+            if events is not None:
+                e = torch.cuda.Event(enable_timing=True); e.record(); events.append(e)
+        mark()
         fe._check(L.fastecc_b200_rs_encode_shard_pass_p2p(X, self._yp, self.N, self.G, self.rank, self.S, self.S, 0, st))
+        mark()
         self._barrier()
+        mark()
         fe._check(L.fastecc_b200_rs_encode_shard_pass_p2p(Y, self._xp, self.N, self.G, self.rank, self.S, self.S, 1, st))
+        mark()
         self._barrier()
+        mark()
         fe._check(L.fastecc_b200_rs_encode_shard_pass_p2p(X, self._xp, self.N, self.G, self.rank, self.S, self.S, 2, st))
+        mark()
         return self.x
 
     def close(self):

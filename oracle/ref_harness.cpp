@@ -70,6 +70,13 @@ static void run_flat(uint32_t* flat, size_t N, size_t SIZE, int what, int inv)
 }
 void ref_mfa_ntt_flat  (uint32_t* flat, size_t N, size_t SIZE, int inv) { run_flat(flat,N,SIZE,0,inv); }
 void ref_rs_encode_flat(uint32_t* flat, size_t N, size_t SIZE)          { run_flat(flat,N,SIZE,1,0); }
+void ref_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 int  ref_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

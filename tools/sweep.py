@@ -1,0 +1,53 @@
+#!/usr/bin/env python
+"""Device-resident timing sweep over the BASELINE parity configs (configs 1, 3 and the NTT sweep 5):
+encode at N = 2^7 .. 2^19 and forward NTT at N = 2^10 .. 2^20, 4096-byte blocks, CUDA events around `reps` back-to-back
+calls.  Arrays below ~100 MB stay in the 126 MB L2 between calls (marked); the small orders are launch-latency bound.
+Prints one JSON line per point."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import numpy as np
+import torch
+
+import fastecc_b200 as fe
+
+P = 0xFFF00001
+
+
+def timed(fn, reps):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def main():
+    fe.init(0)
+    S = 1024
+    for op, Ls in (("encode", range(7, 20)), ("ntt", range(10, 21))):
+        for L in Ls:
+            N = 1 << L
+            x = (torch.arange(N * S, device="cuda", dtype=torch.int64) % P).to(torch.int32).view(N, S)
+            reps = max(5, min(200, int(2e9 // (N * S * 4))))
+            ms = timed((lambda: fe.rs_encode_dev(x)) if op == "encode" else (lambda: fe.ntt_dev(x, False)), reps)
+            nbytes = N * S * 4
+            print(json.dumps({"op": op, "log_n": L, "block_bytes": 4096, "array_MiB": nbytes / 2**20, "ms": round(ms, 5), "reps": reps,
+                              "GBps_read_plus_write": round(2 * nbytes / ms / 1e6, 1),
+                              "MiBps_reference_convention": round((2 if op == "encode" else 1) * nbytes / 2**20 / ms * 1e3),
+                              "l2_resident": nbytes < 100e6}), flush=True)
+            del x
+            torch.cuda.empty_cache()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
