@@ -211,7 +211,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
     return 0
 
 
@@ -336,7 +336,7 @@ def run_b200_arm(args):
             out["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = quick_cpu_baseline(args)
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -411,15 +411,37 @@ def run_sharded(args, fe, rank, world, local, dev):
         }
         if phases:
             out["phases_ms_rank0"] = phases
-        print(json.dumps(out), flush=True)
+        emit(out)
     if fused:
         enc.close()
     dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """Libraries write banners to stdout (torch prints "NCCL version ..." when the first communicator is created).  The
+    contract is ONE JSON line there, so file descriptor 1 points at stderr until emit() prints the result."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(obj), flush=True)
+    if _REAL_STDOUT is not None:
+        os.dup2(2, 1)
+
+
 def main():
     args = parse_args()
+    guard_stdout()
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_b200_arm(args)
