@@ -10,7 +10,7 @@
 // Storage is the TMA tile itself, in its hardware-swizzled layout: natural row order, 64-byte rows with
 // CU_TENSOR_MAP_SWIZZLE_64B (LR = 10), or column blocks of 128-byte rows with SWIZZLE_128B (LR <= 9).  A warp only
 // ever touches the cells of its own columns, in three patterns, each with lanes <-> consecutive rows so that the
-// swizzle spreads them over the banks (conflict-free for 128-byte rows, 2-way for 64-byte rows; scratch/banksim.py):
+// swizzle spreads them over the banks (conflict-free for 128-byte rows, 2-way for 64-byte rows; tools/banksim.py):
 //   natural   row = k*J + jx                       (first read: slot (j0<<5)|i holds input bitrev(slot), j0 = bitrev(jx);
 //                                                   last write: output index jx + i*J)
 //   exchange  row = phi(slot), written as slot (bitrev(jx)<<5)|i, read as slot jx | i<<(LR-5), with

@@ -1,6 +1,6 @@
 #!/bin/bash
 # rebuild the library and summarise the pass kernels' SASS (registers, spills, size, opcode mix)
-cd /root/repo
+cd "$(dirname "$0")/.."
 python fastecc_b200/build.py --force 2>&1 | grep -E "error|spill|Compiling.*ntt_pass" | paste - - | sed 's/ptxas info    ://g; s/Compiling entry function//; s/for .sm_100a.//' | grep -E "Li10ELi1|Li9ELi2|error"
 cuobjdump -sass fastecc_b200/libfastecc_b200.so > /tmp/all.sass
 for pat in "ILi10ELi1ELi1" "ILi9ELi2ELi0"; do
