@@ -51,6 +51,8 @@ def lib() -> ctypes.CDLL:
         L.fastecc_b200_rs_encode.argtypes = [vp, sz, sz]; L.fastecc_b200_rs_encode.restype = ci
         L.fastecc_b200_ntt_u32_dev.argtypes = [vp, sz, sz, sz, ci, vp]; L.fastecc_b200_ntt_u32_dev.restype = ci
         L.fastecc_b200_rs_encode_dev.argtypes = [vp, sz, sz, sz, vp]; L.fastecc_b200_rs_encode_dev.restype = ci
+        L.fastecc_b200_rs_encode_asym.argtypes = [vp, sz, sz, sz]; L.fastecc_b200_rs_encode_asym.restype = ci
+        L.fastecc_b200_rs_encode_asym_dev.argtypes = [vp, sz, sz, sz, sz, vp]; L.fastecc_b200_rs_encode_asym_dev.restype = ci
         L.fastecc_b200_rs_encode_shard_pass.argtypes = [vp, sz, ci, ci, sz, sz, ci, vp]; L.fastecc_b200_rs_encode_shard_pass.restype = ci
         L.fastecc_b200_rs_encode_shard_pass_p2p.argtypes = [vp, vp, sz, ci, ci, sz, sz, ci, vp]; L.fastecc_b200_rs_encode_shard_pass_p2p.restype = ci
         L.fastecc_b200_dev_alloc.argtypes = [sz]; L.fastecc_b200_dev_alloc.restype = vp
@@ -141,6 +143,14 @@ def EncodeReedSolomon_body(data: Blocks, N: int, SIZE: int) -> None:
     del keep
 
 
+def EncodeReedSolomon_asym(data: Blocks, N: int, M: int, SIZE: int) -> None:
+    """N data blocks -> M = N/2^k parity blocks in data[0..M): parity block j' = block (N/M)*j' of the full encode
+    (the even points of the second transform, RS.cpp:65-66)."""
+    tab, keep = _pointer_table(data, N, SIZE)
+    _check(lib().fastecc_b200_rs_encode_asym(tab.ctypes.data, N, M, SIZE))
+    del keep
+
+
 # ---- device-resident entry points (torch tensors are used only as owners of device memory) -----------------------
 def _dev_args(t):
     import torch
@@ -157,6 +167,12 @@ def ntt_dev(t, inverse: bool = False) -> None:
 def rs_encode_dev(t) -> None:
     ptr, N, size, pitch, stream = _dev_args(t)
     _check(lib().fastecc_b200_rs_encode_dev(ptr, N, size, pitch, stream))
+
+
+def rs_encode_asym_dev(t, M: int) -> None:
+    """Rows [0, M) of t receive the M parity blocks; the other rows are undefined afterwards."""
+    ptr, N, size, pitch, stream = _dev_args(t)
+    _check(lib().fastecc_b200_rs_encode_asym_dev(ptr, N, M, size, pitch, stream))
 
 
 def reference_hash(data: np.ndarray) -> int:

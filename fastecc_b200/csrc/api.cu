@@ -98,6 +98,39 @@ int run_aligned(Context* c, uint32_t* x, size_t N, size_t size, size_t pitch, in
     return 0;
 }
 
+// N data blocks -> M = N / 2^k parity blocks in rows [0, M) of x (rows [M, N) are left undefined).
+int run_aligned_asym(Context* c, uint32_t* x, size_t N, size_t M, size_t size, size_t pitch, cudaStream_t st)
+{
+    if (M == N) return run_aligned(c, x, N, size, pitch, 2, st);
+    size_t M0 = N;                                        // what the passes produce; M0 >= M
+    if (N > ((size_t)1 << kMaxLogR)) {
+        M0 = M;
+        while (!asym_native(N, M0)) M0 *= 2;              // M0 = max(M, N1)
+        CUDA_TRY(c->scratch.reserve(N * pitch * sizeof(uint32_t)));
+        Buffers b{x, (uint32_t*)c->scratch.p, c->d_tw, (uint32_t)pitch, (uint32_t)size};
+        std::vector<PassParams> plan = plan_encode_asym(b, N, M0);
+        std::vector<DevBuf>& tabs = c->tables[0x40000000u | ilog2(N / M0) << 8 | ilog2(N)];
+        if (tabs.empty()) {
+            tabs.resize(plan.size());
+            for (size_t i = 0; i < plan.size(); ++i) {
+                CUDA_TRY(tabs[i].reserve(table_bytes(plan[i])));
+                CUDA_TRY(launch_build_tables(plan[i], (uint4*)tabs[i].p, st)); g_launches++;
+            }
+        }
+        for (size_t i = 0; i < plan.size(); ++i) {
+            plan[i].tables = (const uint4*)tabs[i].p;
+            plan[i].table_set_stride = table_sets(plan[i]) > 1 ? (plan[i].nxf << plan[i].log_r) : 0u;
+            CUDA_TRY(launch_pass(plan[i], c->num_sms, st)); g_launches++;
+        }
+    } else if (int rc = run_aligned(c, x, N, size, pitch, 2, st)) return rc;
+    if (M0 != M) {                                        // keep every (M0/M)-th parity block: gather through the scratch buffer
+        CUDA_TRY(c->scratch.reserve(M * pitch * sizeof(uint32_t)));
+        CUDA_TRY(cudaMemcpy2DAsync(c->scratch.p, pitch * 4, x, (M0 / M) * pitch * 4, size * 4, M, cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(cudaMemcpy2DAsync(x, pitch * 4, c->scratch.p, pitch * 4, size * 4, M, cudaMemcpyDeviceToDevice, st));
+    }
+    return 0;
+}
+
 int run_dev(uint32_t* d, size_t N, size_t size, size_t pitch, int mode, void* stream, const char* who)
 {
     Context* c = g_ctx;
@@ -228,6 +261,44 @@ int fastecc_b200_ntt_u32_dev(uint32_t* d, size_t N, size_t size, size_t pitch, i
 
 int fastecc_b200_rs_encode_dev(uint32_t* d, size_t N, size_t size, size_t pitch, void* stream)
 { return run_dev(d, N, size, pitch, 2, stream, "fastecc_b200_rs_encode_dev"); }
+
+int fastecc_b200_rs_encode_asym_dev(uint32_t* d, size_t N, size_t M, size_t size, size_t pitch, void* stream)
+{
+    const char* who = "fastecc_b200_rs_encode_asym_dev";
+    Context* c = g_ctx;
+    if (!c) return fail(FASTECC_B200_ENOINIT, "%s: call fastecc_b200_init() first", who);
+    if (!d) return fail(FASTECC_B200_EINVAL, "%s: null device pointer", who);
+    if (int rc = check_shape(N, size, FASTECC_B200_MAX_LOG_N_ENCODE, who)) return rc;
+    if (!is_pow2(M) || M > N) return fail(FASTECC_B200_EINVAL, "%s: M=%zu must be a power of two in [1, N]", who, M);
+    if (pitch < size || pitch % 4 || ((uintptr_t)d) % 16) return fail(FASTECC_B200_EINVAL, "%s: needs pitch_words >= SIZE_words, pitch %% 4 == 0 and a 16-byte aligned buffer", who);
+    if ((unsigned long long)N * (pitch / 4) >= (1ull << 32)) return fail(FASTECC_B200_EINVAL, "%s: buffer too large (32-bit chunk indexing)", who);
+    return run_aligned_asym(c, d, N, M, size, pitch, (cudaStream_t)stream);
+}
+
+int fastecc_b200_rs_encode_asym(uint32_t** data, size_t N, size_t M, size_t size)
+{
+    const char* who = "fastecc_b200_rs_encode_asym";
+    Context* c = g_ctx;
+    if (!c) return fail(FASTECC_B200_ENOINIT, "%s: call fastecc_b200_init() first", who);
+    if (!data) return fail(FASTECC_B200_EINVAL, "%s: null block table", who);
+    if (int rc = check_shape(N, size, FASTECC_B200_MAX_LOG_N_ENCODE, who)) return rc;
+    if (!is_pow2(M) || M > N) return fail(FASTECC_B200_EINVAL, "%s: M=%zu must be a power of two in [1, N]", who, M);
+    for (size_t i = 0; i < N; i++) if (!data[i]) return fail(FASTECC_B200_EINVAL, "%s: data[%zu] is null", who, i);
+    const size_t pitch = (size + 3) / 4 * 4;
+    CUDA_TRY(c->staging.reserve(N * pitch * sizeof(uint32_t)));
+    uint32_t* dv = (uint32_t*)c->staging.p;
+    cudaStream_t st = c->stream;
+    bool contiguous = true;
+    for (size_t i = 1; i < N; i++) if (data[i] != data[0] + i * size) { contiguous = false; break; }
+    if (pitch != size) CUDA_TRY(cudaMemsetAsync(dv, 0, N * pitch * sizeof(uint32_t), st));
+    if (contiguous) CUDA_TRY(cudaMemcpy2DAsync(dv, pitch * 4, data[0], size * 4, size * 4, N, cudaMemcpyHostToDevice, st));
+    else for (size_t i = 0; i < N; i++) CUDA_TRY(cudaMemcpyAsync(dv + i * pitch, data[i], size * 4, cudaMemcpyHostToDevice, st));
+    if (int rc = run_aligned_asym(c, dv, N, M, size, pitch, st)) return rc;
+    if (contiguous) CUDA_TRY(cudaMemcpy2DAsync(data[0], size * 4, dv, pitch * 4, size * 4, M, cudaMemcpyDeviceToHost, st));
+    else for (size_t i = 0; i < M; i++) CUDA_TRY(cudaMemcpyAsync(data[i], dv + i * pitch, size * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
 
 int fastecc_b200_rs_encode_shard_pass(uint32_t* d_local, size_t N, int n_ranks, int rank, size_t size, size_t pitch, int which, void* stream)
 {

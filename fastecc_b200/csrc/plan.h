@@ -142,6 +142,35 @@ inline std::vector<PassParams> plan_encode(const Buffers& b, size_t N)
     return v;
 }
 
+// Asymmetric encode: N data blocks -> M = N / 2^k parity blocks, parity'[j'] = parity[2^k * j'] of the full encode (the even
+// points of the second transform, RS.cpp:65-66, NTT.md:46-49).  With output index j = j1*N2 + j2, the wanted outputs are
+// the row sets j2 = 2^k * j2' of pass D: D runs on N2 / 2^k sets only and writes its result compactly (row j1*N2' + j2').
+// A is unchanged; BC writes to the scratch buffer b.y because D now reads rows that its compact output would overwrite.
+// Needs the two-level decomposition and M >= N1 (every wanted output still has j2 as its low digit); smaller M and
+// N <= 1024 are served by the caller from the smallest supported M (api.cu).  The first transform and the C half of BC
+// are not shortened yet (folding the coefficients before C needs the scaling as an explicit product first).
+inline bool asym_native(size_t N, size_t M)
+{
+    const uint32_t LN = ilog2(N);
+    if (LN <= (uint32_t)kMaxLogR || M >= N) return false;
+    return M >= ((size_t)1 << split_l1(LN));
+}
+inline std::vector<PassParams> plan_encode_asym(const Buffers& b, size_t N, size_t M)
+{
+    std::vector<PassParams> v = plan_encode(b, N);                     // A, BC, D
+    const uint32_t LN = ilog2(N), L1 = split_l1(LN), L2 = LN - L1;
+    const uint32_t N2 = 1u << L2, dec = (uint32_t)(N / M), N2s = N2 / dec;
+    const long long q = (long long)(kM / (2 * N));
+    v[1].dst = b.y;
+    PassParams& d = v[2];
+    d.src = b.y; d.dst = b.x;
+    d.nsets = N2s;
+    d.src_set_stride = dec; d.src_row_stride = N2;
+    d.dst_set_stride = 1;   d.dst_row_stride = N2s;
+    d.xf[0] = Xform{emod(2 * q * (long long)N2), emod(q), emod(2 * q * (long long)dec)};
+    return v;
+}
+
 // One transform sharded over G GPUs (BASELINE config 4).  Blocks are dealt cyclically: global block
 // i = l*G + g is local block l of rank g, for the data going in and for the parity coming out.  With N2 % G == 0 every
 // row set of pass A (fixed n2) and of pass D (fixed j2) is local to rank n2 % G resp. j2 % G, and every row set of

@@ -61,6 +61,15 @@ int fastecc_b200_rs_encode(uint32_t** data, size_t N, size_t SIZE_words);
 int fastecc_b200_ntt_u32_dev  (uint32_t* d_blocks, size_t N, size_t SIZE_words, size_t pitch_words, int inverse, void* stream);
 int fastecc_b200_rs_encode_dev(uint32_t* d_blocks, size_t N, size_t SIZE_words, size_t pitch_words, void* stream);
 
+/* ---- fewer parity blocks than data blocks ------------------------------------------------------
+ * The reference only describes this (RS.cpp:65-66, NTT.md:46-49: "in order to compute only even-indexed points ...").
+ * N data blocks in, M = N / 2^k parity blocks out: parity block j' is parity block (N/M)*j' of the full N -> N encode,
+ * i.e. the value of the data polynomial at root_2N^(2*(N/M)*j' + 1).  On return data[j'], j' < M, hold the parity;
+ * blocks M .. N-1 are undefined (host variant: left untouched).  1 <= M <= N <= 2^19, both powers of two.
+ * The _dev variant needs a 16-byte aligned buffer and pitch_words % 4 == 0. */
+int fastecc_b200_rs_encode_asym    (uint32_t** data, size_t N, size_t M, size_t SIZE_words);
+int fastecc_b200_rs_encode_asym_dev(uint32_t* d_blocks, size_t N, size_t M, size_t SIZE_words, size_t pitch_words, void* stream);
+
 /* ---- one transform sharded over several GPUs (one process per GPU; BASELINE config 4) ---------------------------
  * Global block i = l*n_ranks + rank is local block l (data in, parity out).  An encode is: pass 0 on every rank,
  * all-to-all of whole blocks, pass 1, all-to-all, pass 2 -- the exchange is the caller's (fastecc_b200/sharded.py does it

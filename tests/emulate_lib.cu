@@ -24,6 +24,13 @@ extern "C" int emu_rs_encode_shard_pass_p2p(const uint32_t* src, uint32_t* const
                                        N, (uint32_t)n_ranks, (uint32_t)rank, which));
     return 0;
 }
+extern "C" int emu_rs_encode_asym(uint32_t* x, uint32_t* y, size_t N, size_t M, size_t size, size_t pitch)
+{
+    if (!asym_native(N, M)) return -1;
+    Buffers b{x, y, reinterpret_cast<const uint4*>(power_table().data()), (uint32_t)pitch, (uint32_t)size};
+    for (auto& p : plan_encode_asym(b, N, M)) emulate_pass(p);
+    return 0;
+}
 extern "C" int emu_rs_encode(uint32_t* x, size_t N, size_t size, size_t pitch)
 {
     Buffers b{x, nullptr, reinterpret_cast<const uint4*>(power_table().data()), (uint32_t)pitch, (uint32_t)size};

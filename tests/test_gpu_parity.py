@@ -223,6 +223,56 @@ def test_many_tiles_column_sample(fecc, oracle, L, S):
     torch.cuda.empty_cache()
 
 
+@pytest.mark.parametrize("L,K,S", [(3, 1, 4), (4, 4, 8), (7, 2, 16), (10, 1, 24), (11, 1, 16), (12, 2, 40), (12, 8, 8), (13, 13, 4), (14, 3, 12), (16, 1, 16)])
+def test_dev_asymmetric_encode_is_a_subset_of_the_full_encode(fecc, oracle, L, K, S):
+    """N data -> M = N/2^K parity blocks (RS.cpp:65-66): block j' must equal block 2^K * j' of the
+    oracle's full encode.  Covers the native path (D on a subset of row sets), the gather path (M < N1, N <= 1024)."""
+    N, M = 1 << L, 1 << (L - K)
+    a = ol.fill_B(oracle, N, S)
+    want = ol.o_encode(oracle, a)[::N // M]
+    t = to_dev(a)
+    fecc.rs_encode_asym_dev(t, M)
+    assert np.array_equal(to_host(t[:M]), want)
+
+
+@pytest.mark.parametrize("L,K,S", [(5, 2, 3), (9, 1, 513), (12, 1, 64), (13, 2, 1024)])
+def test_host_asymmetric_encode(fecc, oracle, L, K, S):
+    N, M = 1 << L, 1 << (L - K)
+    a = ol.fill_B(oracle, N, S)
+    want = ol.o_encode(oracle, a)[::N // M]
+    blocks = a.copy()
+    fecc.EncodeReedSolomon_asym(blocks, N, M, S)
+    assert np.array_equal(blocks[:M], want)
+    assert np.array_equal(blocks[M:], a[M:])                  # blocks M..N-1 are not written back
+
+
+def test_full_size_asymmetric_encode(fecc, oracle):
+    """2^19 data blocks -> 2^18 and 2^16 parity blocks of 4096 bytes == every 2nd / 8th block of the full encode, whose
+    hash is pinned to the reference's (test_headline_config_encode_goldens)."""
+    import torch
+    N, S = 1 << 19, 1024
+    a = torch.from_numpy(ol.fill_A(oracle, N, S).view(np.int32)).cuda()
+    full = a.clone()
+    fecc.rs_encode_dev(full)
+    assert ol.ohash(oracle, to_host(full)) == [g for g in G["encode_fillA"] if g[0] == 19][0][3]
+    for K in (1, 3):
+        M = N >> K
+        t = a.clone()
+        fecc.rs_encode_asym_dev(t, M)
+        assert bool((t[:M] == full[::1 << K]).all())
+        del t
+    del a, full
+    torch.cuda.empty_cache()
+
+
+def test_asymmetric_argument_validation(fecc):
+    import torch
+    t = torch.zeros((64, 8), dtype=torch.int32, device="cuda")
+    for M in (0, 3, 128):
+        with pytest.raises(Exception):
+            fecc.rs_encode_asym_dev(t, M)
+
+
 def test_argument_validation(fecc):
     a = np.zeros((3, 4), dtype=np.uint32)
     with pytest.raises(fecc.FastEccError) as e:

@@ -46,6 +46,14 @@ def main():
                               "l2_resident": nbytes < 100e6}), flush=True)
             del x
             torch.cuda.empty_cache()
+    N = 1 << 19
+    for K in (1, 2, 3, 6):
+        x = (torch.arange(N * S, device="cuda", dtype=torch.int64) % P).to(torch.int32).view(N, S)
+        ms = timed(lambda: fe.rs_encode_asym_dev(x, N >> K), 5)
+        print(json.dumps({"op": "encode_asym", "log_n": 19, "log_m": 19 - K, "block_bytes": 4096, "ms": round(ms, 5),
+                          "GBps_data_plus_parity": round((N + (N >> K)) * S * 4 / ms / 1e6, 1)}), flush=True)
+        del x
+        torch.cuda.empty_cache()
     return 0
 
 
