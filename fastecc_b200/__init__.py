@@ -53,6 +53,8 @@ def lib() -> ctypes.CDLL:
         L.fastecc_b200_rs_encode_dev.argtypes = [vp, sz, sz, sz, vp]; L.fastecc_b200_rs_encode_dev.restype = ci
         L.fastecc_b200_rs_encode_asym.argtypes = [vp, sz, sz, sz]; L.fastecc_b200_rs_encode_asym.restype = ci
         L.fastecc_b200_rs_encode_asym_dev.argtypes = [vp, sz, sz, sz, sz, vp]; L.fastecc_b200_rs_encode_asym_dev.restype = ci
+        L.fastecc_b200_bytes_to_gfp_dev.argtypes = [vp, vp, sz, sz, sz, vp]; L.fastecc_b200_bytes_to_gfp_dev.restype = ci
+        L.fastecc_b200_gfp_to_bytes_dev.argtypes = [vp, vp, sz, sz, sz, vp]; L.fastecc_b200_gfp_to_bytes_dev.restype = ci
         L.fastecc_b200_rs_encode_shard_pass.argtypes = [vp, sz, ci, ci, sz, sz, ci, vp]; L.fastecc_b200_rs_encode_shard_pass.restype = ci
         L.fastecc_b200_rs_encode_shard_pass_p2p.argtypes = [vp, vp, sz, ci, ci, sz, sz, ci, vp]; L.fastecc_b200_rs_encode_shard_pass_p2p.restype = ci
         L.fastecc_b200_dev_alloc.argtypes = [sz]; L.fastecc_b200_dev_alloc.restype = vp
@@ -173,6 +175,26 @@ def rs_encode_asym_dev(t, M: int) -> None:
     """Rows [0, M) of t receive the M parity blocks; the other rows are undefined afterwards."""
     ptr, N, size, pitch, stream = _dev_args(t)
     _check(lib().fastecc_b200_rs_encode_asym_dev(ptr, N, M, size, pitch, stream))
+
+
+def bytes_to_gfp_dev(raw, words=None):
+    """raw: 2-D CUDA uint8 tensor [n_blocks, 4*W] (contiguous) -> int32 tensor [n_blocks, pitch] with words 0..W of every row
+    set (GF.md:72-104 recoding: all of them < P).  pitch = W + 4 keeps rows 16-byte aligned."""
+    import torch
+    n, nbytes = raw.shape
+    W = nbytes // 4
+    if words is None:
+        words = torch.zeros((n, W + 4), dtype=torch.int32, device=raw.device)
+    _check(lib().fastecc_b200_bytes_to_gfp_dev(raw.data_ptr(), words.data_ptr(), n, W, words.stride(0), torch.cuda.current_stream(raw.device).cuda_stream))
+    return words
+
+
+def gfp_to_bytes_dev(words, W: int):
+    import torch
+    n = words.shape[0]
+    raw = torch.empty((n, 4 * W), dtype=torch.uint8, device=words.device)
+    _check(lib().fastecc_b200_gfp_to_bytes_dev(words.data_ptr(), raw.data_ptr(), n, W, words.stride(0), torch.cuda.current_stream(words.device).cuda_stream))
+    return raw
 
 
 def reference_hash(data: np.ndarray) -> int:

@@ -3,6 +3,7 @@
 #include "plan.h"
 #include "ntt_pass.h"
 #include "small_dft.h"
+#include "byte_recode.h"
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdarg>
@@ -261,6 +262,29 @@ int fastecc_b200_ntt_u32_dev(uint32_t* d, size_t N, size_t size, size_t pitch, i
 
 int fastecc_b200_rs_encode_dev(uint32_t* d, size_t N, size_t size, size_t pitch, void* stream)
 { return run_dev(d, N, size, pitch, 2, stream, "fastecc_b200_rs_encode_dev"); }
+
+static int recode_args(const void* a, const void* b, size_t n_blocks, size_t W, size_t pitch, const char* who)
+{
+    if (!g_ctx) return fail(FASTECC_B200_ENOINIT, "%s: call fastecc_b200_init() first", who);
+    if (!a || !b) return fail(FASTECC_B200_EINVAL, "%s: null device pointer", who);
+    if (W == 0 || W > 1024 || W % 4) return fail(FASTECC_B200_EINVAL, "%s: words_per_block=%zu must be a multiple of 4 in [4, 1024] (10-bit positions, GF.md:84)", who, W);
+    if (pitch < W + 1 || pitch % 4) return fail(FASTECC_B200_EINVAL, "%s: pitch_words must be >= words_per_block + 1 and a multiple of 4", who);
+    if (((uintptr_t)a) % 16 || ((uintptr_t)b) % 16) return fail(FASTECC_B200_EINVAL, "%s: buffers must be 16-byte aligned", who);
+    if (n_blocks >= (1ull << 31)) return fail(FASTECC_B200_EINVAL, "%s: too many blocks", who);
+    return 0;
+}
+int fastecc_b200_bytes_to_gfp_dev(const void* d_bytes, uint32_t* d_words, size_t n_blocks, size_t W, size_t pitch, void* stream)
+{
+    if (int rc = recode_args(d_bytes, d_words, n_blocks, W, pitch, "fastecc_b200_bytes_to_gfp_dev")) return rc;
+    CUDA_TRY(launch_bytes_to_gfp(d_bytes, d_words, n_blocks, (uint32_t)W, pitch, (cudaStream_t)stream)); g_launches++;
+    return 0;
+}
+int fastecc_b200_gfp_to_bytes_dev(const uint32_t* d_words, void* d_bytes, size_t n_blocks, size_t W, size_t pitch, void* stream)
+{
+    if (int rc = recode_args(d_words, d_bytes, n_blocks, W, pitch, "fastecc_b200_gfp_to_bytes_dev")) return rc;
+    CUDA_TRY(launch_gfp_to_bytes(d_words, d_bytes, n_blocks, (uint32_t)W, pitch, (cudaStream_t)stream)); g_launches++;
+    return 0;
+}
 
 int fastecc_b200_rs_encode_asym_dev(uint32_t* d, size_t N, size_t M, size_t size, size_t pitch, void* stream)
 {

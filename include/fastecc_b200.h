@@ -70,6 +70,17 @@ int fastecc_b200_rs_encode_dev(uint32_t* d_blocks, size_t N, size_t SIZE_words, 
 int fastecc_b200_rs_encode_asym    (uint32_t** data, size_t N, size_t M, size_t SIZE_words);
 int fastecc_b200_rs_encode_asym_dev(uint32_t* d_blocks, size_t N, size_t M, size_t SIZE_words, size_t pitch_words, void* stream);
 
+/* ---- arbitrary bytes <-> words below P -----------------------------------------------------------
+ * The reference describes, but does not implement, a bit-optimal recoding (GF.md:72-104, README.md:160-163): the top
+ * 12 bits of the W words of a block are rewritten from base 4096 to base 4095 (no 0xFFF, hence every word < P) using
+ * one extra bit, stored as word W of the block: 4096-byte blocks become 4100-byte (1025-word) blocks to encode.
+ * d_bytes: n_blocks contiguous blocks of 4*W bytes; d_words: n_blocks rows of pitch_words words (>= W+1, % 4 == 0), words
+ * 0..W of a row are meaningful.  W = words_per_block: multiple of 4, <= 1024.  Both buffers 16-byte aligned.
+ * gfp_to_bytes(bytes_to_gfp(x)) == x for every x; parity rows produced by the encoder are NOT recoded data and are
+ * stored as they are (GF.md:101-104). */
+int fastecc_b200_bytes_to_gfp_dev(const void* d_bytes, uint32_t* d_words, size_t n_blocks, size_t words_per_block, size_t pitch_words, void* stream);
+int fastecc_b200_gfp_to_bytes_dev(const uint32_t* d_words, void* d_bytes, size_t n_blocks, size_t words_per_block, size_t pitch_words, void* stream);
+
 /* ---- one transform sharded over several GPUs (one process per GPU; BASELINE config 4) ---------------------------
  * Global block i = l*n_ranks + rank is local block l (data in, parity out).  An encode is: pass 0 on every rank,
  * all-to-all of whole blocks, pass 1, all-to-all, pass 2 -- the exchange is the caller's (fastecc_b200/sharded.py does it

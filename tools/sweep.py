@@ -33,7 +33,8 @@ def timed(fn, reps):
 def main():
     fe.init(0)
     S = 1024
-    for op, Ls in (("encode", range(7, 20)), ("ntt", range(10, 21))):
+    only_extras = "--extras" in sys.argv
+    for op, Ls in (() if only_extras else (("encode", range(7, 20)), ("ntt", range(10, 21)))):
         for L in Ls:
             N = 1 << L
             x = (torch.arange(N * S, device="cuda", dtype=torch.int64) % P).to(torch.int32).view(N, S)
@@ -46,6 +47,17 @@ def main():
                               "l2_resident": nbytes < 100e6}), flush=True)
             del x
             torch.cuda.empty_cache()
+    n, W = 1 << 19, 1024                                      # byte <-> GF(p) recoding, 2 GiB of random bytes (22 % of the blocks need recoding)
+    raw = torch.randint(0, 256, (n, 4 * W), dtype=torch.uint8, device="cuda")
+    words = torch.zeros((n, W + 4), dtype=torch.int32, device="cuda")
+    ms = timed(lambda: fe.bytes_to_gfp_dev(raw, words), 10)
+    print(json.dumps({"op": "bytes_to_gfp", "blocks": n, "block_bytes": 4 * W, "ms": round(ms, 5), "GBps_read_plus_write": round((n * 4 * W + n * 4 * (W + 1)) / ms / 1e6, 1)}), flush=True)
+    back = torch.empty_like(raw)
+    ms = timed(lambda: fe._check(fe.lib().fastecc_b200_gfp_to_bytes_dev(words.data_ptr(), back.data_ptr(), n, W, W + 4, torch.cuda.current_stream().cuda_stream)), 10)
+    print(json.dumps({"op": "gfp_to_bytes", "blocks": n, "block_bytes": 4 * W, "ms": round(ms, 5), "GBps_read_plus_write": round((n * 4 * W + n * 4 * (W + 1)) / ms / 1e6, 1),
+                      "roundtrip_ok": bool((back == raw).all())}), flush=True)
+    del raw, words, back
+    torch.cuda.empty_cache()
     N = 1 << 19
     for K in (1, 2, 3, 6):
         x = (torch.arange(N * S, device="cuda", dtype=torch.int64) % P).to(torch.int32).view(N, S)
