@@ -55,6 +55,9 @@ def lib() -> ctypes.CDLL:
         L.fastecc_b200_rs_encode_asym_dev.argtypes = [vp, sz, sz, sz, sz, vp]; L.fastecc_b200_rs_encode_asym_dev.restype = ci
         L.fastecc_b200_bytes_to_gfp_dev.argtypes = [vp, vp, sz, sz, sz, vp]; L.fastecc_b200_bytes_to_gfp_dev.restype = ci
         L.fastecc_b200_gfp_to_bytes_dev.argtypes = [vp, vp, sz, sz, sz, vp]; L.fastecc_b200_gfp_to_bytes_dev.restype = ci
+        L.fastecc_b200_gf_mul_dev.argtypes = [vp, vp, vp, sz, vp]; L.fastecc_b200_gf_mul_dev.restype = ci
+        L.fastecc_b200_gf_inv_dev.argtypes = [vp, vp, sz, vp]; L.fastecc_b200_gf_inv_dev.restype = ci
+        L.fastecc_b200_row_scale_dev.argtypes = [vp, sz, sz, sz, vp, vp]; L.fastecc_b200_row_scale_dev.restype = ci
         L.fastecc_b200_rs_encode_shard_pass.argtypes = [vp, sz, ci, ci, sz, sz, ci, vp]; L.fastecc_b200_rs_encode_shard_pass.restype = ci
         L.fastecc_b200_rs_encode_shard_pass_p2p.argtypes = [vp, vp, sz, ci, ci, sz, sz, ci, vp]; L.fastecc_b200_rs_encode_shard_pass_p2p.restype = ci
         L.fastecc_b200_dev_alloc.argtypes = [sz]; L.fastecc_b200_dev_alloc.restype = vp

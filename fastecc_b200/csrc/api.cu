@@ -4,6 +4,7 @@
 #include "ntt_pass.h"
 #include "small_dft.h"
 #include "byte_recode.h"
+#include "elementwise.h"
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdarg>
@@ -262,6 +263,31 @@ int fastecc_b200_ntt_u32_dev(uint32_t* d, size_t N, size_t size, size_t pitch, i
 
 int fastecc_b200_rs_encode_dev(uint32_t* d, size_t N, size_t size, size_t pitch, void* stream)
 { return run_dev(d, N, size, pitch, 2, stream, "fastecc_b200_rs_encode_dev"); }
+
+int fastecc_b200_gf_mul_dev(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, void* stream)
+{
+    if (!g_ctx) return fail(FASTECC_B200_ENOINIT, "fastecc_b200_gf_mul_dev: call fastecc_b200_init() first");
+    if (n && (!a || !b || !out)) return fail(FASTECC_B200_EINVAL, "fastecc_b200_gf_mul_dev: null device pointer");
+    CUDA_TRY(launch_gf_mul(a, b, out, n, (cudaStream_t)stream)); g_launches++;
+    return 0;
+}
+int fastecc_b200_gf_inv_dev(const uint32_t* a, uint32_t* out, size_t n, void* stream)
+{
+    if (!g_ctx) return fail(FASTECC_B200_ENOINIT, "fastecc_b200_gf_inv_dev: call fastecc_b200_init() first");
+    if (n && (!a || !out)) return fail(FASTECC_B200_EINVAL, "fastecc_b200_gf_inv_dev: null device pointer");
+    CUDA_TRY(launch_gf_inv(a, out, n, (cudaStream_t)stream)); g_launches++;
+    return 0;
+}
+int fastecc_b200_row_scale_dev(uint32_t* d, size_t n_rows, size_t size, size_t pitch, const uint32_t* d_consts, void* stream)
+{
+    const char* who = "fastecc_b200_row_scale_dev";
+    if (!g_ctx) return fail(FASTECC_B200_ENOINIT, "%s: call fastecc_b200_init() first", who);
+    if (!d || !d_consts) return fail(FASTECC_B200_EINVAL, "%s: null device pointer", who);
+    if (size == 0 || pitch < size || pitch % 4 || ((uintptr_t)d) % 16) return fail(FASTECC_B200_EINVAL, "%s: needs SIZE >= 1, pitch_words >= SIZE, pitch %% 4 == 0 and a 16-byte aligned buffer (pad words of a row are scaled too)", who);
+    if (pitch / 4 >= (1ull << 32)) return fail(FASTECC_B200_EINVAL, "%s: rows too long", who);
+    CUDA_TRY(launch_row_scale(d, n_rows, (uint32_t)((size + 3) / 4), (uint32_t)(pitch / 4), d_consts, g_ctx->num_sms, (cudaStream_t)stream)); g_launches++;
+    return 0;
+}
 
 static int recode_args(const void* a, const void* b, size_t n_blocks, size_t W, size_t pitch, const char* who)
 {

@@ -81,6 +81,14 @@ int fastecc_b200_rs_encode_asym_dev(uint32_t* d_blocks, size_t N, size_t M, size
 int fastecc_b200_bytes_to_gfp_dev(const void* d_bytes, uint32_t* d_words, size_t n_blocks, size_t words_per_block, size_t pitch_words, void* stream);
 int fastecc_b200_gfp_to_bytes_dev(const uint32_t* d_words, void* d_bytes, size_t n_blocks, size_t words_per_block, size_t pitch_words, void* stream);
 
+/* ---- element-wise helpers around the transforms (erasure decoding) --------------------------------
+ * GF_Mul (GF(p).cpp:110-127) and GF_Inv (GF(p).cpp:293-297, x^(P-2); 0 -> 0) on device vectors of n words, and the shape
+ * of the reference's scaling loop (RS.cpp:51-59) with an arbitrary constant per block: block i *= d_consts[i].
+ * Inputs are taken mod P, results are canonical.  row_scale: 16-byte aligned buffer, pitch_words % 4 == 0. */
+int fastecc_b200_gf_mul_dev(const uint32_t* d_a, const uint32_t* d_b, uint32_t* d_out, size_t n, void* stream);
+int fastecc_b200_gf_inv_dev(const uint32_t* d_a, uint32_t* d_out, size_t n, void* stream);
+int fastecc_b200_row_scale_dev(uint32_t* d_blocks, size_t n_rows, size_t SIZE_words, size_t pitch_words, const uint32_t* d_consts, void* stream);
+
 /* ---- one transform sharded over several GPUs (one process per GPU; BASELINE config 4) ---------------------------
  * Global block i = l*n_ranks + rank is local block l (data in, parity out).  An encode is: pass 0 on every rank,
  * all-to-all of whole blocks, pass 1, all-to-all, pass 2 -- the exchange is the caller's (fastecc_b200/sharded.py does it

@@ -58,6 +58,22 @@ def main():
                       "roundtrip_ok": bool((back == raw).all())}), flush=True)
     del raw, words, back
     torch.cuda.empty_cache()
+    from fastecc_b200 import decoder                          # erasure decoding at the headline order: 2^19 data + 2^19 parity blocks of 4 KiB
+    N2 = 1 << 20
+    code = (torch.arange(N2 * S, device="cuda", dtype=torch.int64) % P).to(torch.int32).view(N2, S)
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    erased = torch.sort(torch.randperm(N2, device="cuda", generator=g)[:N2 // 2]).values.cpu().tolist()
+    torch.cuda.synchronize()
+    import time
+    t0 = time.perf_counter()
+    pat = decoder.ErasurePattern(N2, erased, code.device)
+    torch.cuda.synchronize()
+    t_pat = (time.perf_counter() - t0) * 1e3
+    ms = timed(lambda: pat.recover(code), 3)                 # (timing only: the workspace is not a code word after the first call)
+    print(json.dumps({"op": "decode", "log_n": 19, "erased": N2 // 2, "block_bytes": 4096, "pattern_setup_ms_wall": round(t_pat, 1), "recover_ms": round(ms, 4),
+                      "GBps_codeword_bytes": round(N2 * S * 4 / ms / 1e6, 1)}), flush=True)
+    del code, pat
+    torch.cuda.empty_cache()
     N = 1 << 19
     for K in (1, 2, 3, 6):
         x = (torch.arange(N * S, device="cuda", dtype=torch.int64) % P).to(torch.int32).view(N, S)
