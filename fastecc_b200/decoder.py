@@ -57,9 +57,20 @@ class CudaBackend:
             t.copy_(self.gf_mul(t, consts.view(-1, 1).expand_as(t)))
 
 
-def _to_i32(torch, values, device):
-    """python ints in [0, 2^32) -> int32 tensor holding the same bit patterns"""
-    return torch.tensor([v - (1 << 32) if v >= (1 << 31) else v for v in values], dtype=torch.int32, device=device)
+def _const_i32(torch, value: int, n: int, device):
+    """n copies of the 32-bit pattern `value` (an int in [0, 2^32)) as an int32 tensor"""
+    return torch.full((n,), value - (1 << 32) if value >= (1 << 31) else value, dtype=torch.int32, device=device)
+
+
+def _positions(torch, erased, n2: int, device):
+    """erased positions (list or tensor) -> validated sorted int64 tensor on `device`"""
+    idx = torch.as_tensor(erased, dtype=torch.long).to(device).view(-1)
+    me = idx.numel()
+    if me > n2 // 2:
+        raise ValueError("at most N = %d of the 2N symbols can be erased, got %d" % (n2 // 2, me))
+    if me and (int(idx.min()) < 0 or int(idx.max()) >= n2 or (me > 1 and not bool((idx[1:] > idx[:-1]).all()))):
+        raise ValueError("erased: sorted distinct positions in [0, 2N)")
+    return idx
 
 
 def root_powers(n2: int, device, be):
@@ -77,7 +88,8 @@ def root_powers(n2: int, device, be):
 def locator_coefficients(erased, n2: int, device, be):
     """Coefficients l_0 .. l_{n2-1} (zero padded) of prod (x - rho^e), e in `erased` (sorted, distinct, at most n2/2)."""
     import torch
-    me = len(erased)
+    idx = _positions(torch, erased, n2, device)
+    me = idx.numel()
     lc = torch.zeros(n2, dtype=torch.int32, device=device)
     if me == 0:
         lc[0] = 1
@@ -86,8 +98,7 @@ def locator_coefficients(erased, n2: int, device, be):
     while mp < me:
         mp *= 2
     pw = root_powers(n2, device, be)
-    idx = torch.as_tensor(erased, dtype=torch.long, device=device)
-    minus = be.gf_mul(pw[idx], _to_i32(torch, [P - 1] * me, device))           # -rho^e
+    minus = be.gf_mul(pw[idx], _const_i32(torch, P - 1, me, device))           # -rho^e
     polys = torch.zeros((2, mp), dtype=torch.int32, device=device)             # column = one factor: [-rho^e, 1]; padding: [1, 0]
     polys[0, :me] = minus
     polys[1, :me] = 1
@@ -101,7 +112,7 @@ def locator_coefficients(erased, n2: int, device, be):
         b = be.gf_mul(a[:, 0::2], a[:, 1::2])
         be.ntt(b, True)
         inv = pow(4 * d, P - 2, P)
-        be.row_scale(b, _to_i32(torch, [inv] * (4 * d), device))
+        be.row_scale(b, _const_i32(torch, inv, 4 * d, device))
         polys = b[:2 * d + 1].contiguous()
         d *= 2
     lc[:mp + 1] = polys[:, 0]
@@ -115,24 +126,22 @@ class ErasurePattern:
     def __init__(self, n2: int, erased, device, be=None):
         import torch
         self.be = be or CudaBackend()
-        me = len(erased)
         if n2 < 2 or n2 & (n2 - 1) or n2 > (1 << 20):
             raise ValueError("the code word must have 2N = 2 .. 2^20 rows (a power of two)")
-        if me > n2 // 2 or any(erased[i] >= erased[i + 1] for i in range(me - 1)) or (me and (erased[0] < 0 or erased[-1] >= n2)):
-            raise ValueError("erased: at most N sorted distinct positions in [0, 2N)")
+        self.idx = _positions(torch, erased, n2, device)
+        me = self.idx.numel()
         self.n2, self.me = n2, me
         if me == 0:
             return
         be = self.be
-        self.idx = torch.as_tensor(erased, dtype=torch.long, device=device)
         self.pos = torch.arange(n2, dtype=torch.int32, device=device)
-        lc = locator_coefficients(erased, n2, device, be)
+        lc = locator_coefficients(self.idx, n2, device, be)
         lv = lc.clone().view(n2, 1)
         be.ntt(lv, False)                                                      # l(rho^m): zero exactly on the erased rows
         self.lv = lv.view(-1).contiguous()
         dl = be.gf_mul(lc, self.pos).view(n2, 1)
         be.ntt(dl, False)                                                      # D[j] = rho^j * l'(rho^j)
-        self.ce = be.gf_inv(be.gf_mul(dl.view(-1)[self.idx], _to_i32(torch, [n2] * me, device)))   # 1 / (2N * D[e])
+        self.ce = be.gf_inv(be.gf_mul(dl.view(-1)[self.idx], _const_i32(torch, n2, me, device)))   # 1 / (2N * D[e])
 
     def recover(self, code):
         """code: [2N, S] int32 tensor, arbitrary content in the erased rows; DESTROYED (it is the workspace of the two
