@@ -152,11 +152,22 @@ def load_oracle_port():
     return oracle_lib.load_oracle()
 
 
+def fill_index_mod_p(arr, chunk=1 << 24):
+    """arr.flat[i] = i % P (the reference's fill, RS.cpp:28-29), in slices: no array-sized temporaries (eight ranks fill
+    2 GiB each at the same time in the multi-GPU runs)."""
+    import numpy as np
+    flat = arr.reshape(-1)
+    for lo in range(0, flat.size, chunk):
+        hi = min(lo + chunk, flat.size)
+        flat[lo:hi] = (np.arange(lo, hi, dtype=np.uint64) % P).astype(np.uint32)
+
+
 def cpu_encode_runner(log_n, size_words, calibrate=True):
     """Returns (fn, kind, cores, label): fn() runs one full CPU encode of 2^log_n x size_words in place."""
     import numpy as np
     N = 1 << log_n
-    buf = (np.arange(N * size_words, dtype=np.uint64) % P).astype(np.uint32)
+    buf = np.empty(N * size_words, dtype=np.uint32)
+    fill_index_mod_p(buf)
     r = load_ref_lib()
     if r is not None:
         # T** data, RS.cpp:31-33; left permuted between steps like the reference leaves it
@@ -298,7 +309,7 @@ def run_b200_arm(args):
         if not hptr:
             raise SystemExit("pinned allocation failed")
         harr = np.ctypeslib.as_array((ctypes.c_uint32 * (N * S)).from_address(hptr)).reshape(N, S)
-        harr[:] = (np.arange(N * S, dtype=np.uint64) % P).astype(np.uint32).reshape(N, S)
+        fill_index_mod_p(harr)
         fe.EncodeReedSolomon_body(harr, N, S)                           # warm-up (allocates the device staging buffer)
         barrier()
         t0 = time.perf_counter()
