@@ -30,10 +30,15 @@ METRIC = "rs_encode_GBps_n2^20_k2^19_4KiB_blocks"
 
 def profiled_traffic():
     """DRAM bytes (read + write) per ntt_pass_kernel launch from the committed `ncu --set full` capture of this workload
-    (profiles/*_passes_A_BC_D.csv, newest), averaged over the three passes of an encode; None if absent."""
+    (profiles/*_passes_A_BC_D.csv, highest round / version in the name), averaged over the three passes of an encode; None if absent."""
     import csv
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_v*_passes_A_BC_D.csv")), key=os.path.getmtime)
+    import re
+
+    def version(path):                      # r<round>_ncu_v<kernel version>_passes_A_BC_D.csv: newest round, then newest version
+        m = re.search(r"r(\d+)_ncu_v(\d+)_passes", os.path.basename(path))
+        return (int(m.group(1)), int(m.group(2))) if m else (-1, -1)
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_v*_passes_A_BC_D.csv")), key=version)
     if not files:
         return None, None
     try:
