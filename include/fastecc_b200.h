@@ -104,7 +104,8 @@ int fastecc_b200_rs_encode_shard_pass(uint32_t* d_local, size_t N, int n_ranks, 
  *   which 1: reads the local Y, writes the rows of X on their owners     d_src = Y_local, d_peers[r] = rank r's X
  *   which 2: local, in place on X                                        d_src = X_local, d_peers[rank] = X_local
  * d_peers: HOST array of n_ranks device pointers (own buffer at [rank]).  The caller separates the passes with a
- * cross-rank barrier on the stream (fastecc_b200/sharded.py: a one-word NCCL all-reduce).  n_ranks <= 8, N = 2^15..2^19. */
+ * cross-rank barrier on the stream (fastecc_b200/sharded.py: a one-word NCCL all-reduce).  n_ranks = 2, 4 or 8; N = 2^12..2^19 with
+ * both factors of N = N1*N2 (csrc/plan.h split_l1) at least 32*n_ranks, so that the 32 rows a thread stores go to one rank. */
 int fastecc_b200_rs_encode_shard_pass_p2p(const uint32_t* d_src, uint32_t* const* d_peers, size_t N, int n_ranks, int rank,
                                           size_t SIZE_words, size_t pitch_words, int which, void* stream);
 void* fastecc_b200_dev_alloc(size_t bytes);                       /* cudaMalloc: exportable, unlike a caching-allocator block */
