@@ -66,6 +66,10 @@ def lib() -> ctypes.CDLL:
         L.fastecc_b200_ipc_open.argtypes = [vp, ctypes.POINTER(vp)]; L.fastecc_b200_ipc_open.restype = ci
         L.fastecc_b200_ipc_close.argtypes = [vp]; L.fastecc_b200_ipc_close.restype = ci
         L.fastecc_b200_kernel_launches.argtypes = []; L.fastecc_b200_kernel_launches.restype = ctypes.c_ulonglong
+        L.fastecc_b200_rs_encode_dev_timed.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp]; L.fastecc_b200_rs_encode_dev_timed.restype = ci
+        L.fastecc_b200_shard_geometry.argtypes = [sz, ci, vp, vp, vp]; L.fastecc_b200_shard_geometry.restype = ci
+        L.fastecc_b200_copy2d_async.argtypes = [vp, sz, vp, sz, sz, sz, ci, vp]; L.fastecc_b200_copy2d_async.restype = ci
+        L.fastecc_b200_hash_u32.argtypes = [vp, sz, sz]; L.fastecc_b200_hash_u32.restype = ctypes.c_uint32
         L.fastecc_b200_host_alloc.argtypes = [sz]; L.fastecc_b200_host_alloc.restype = vp
         L.fastecc_b200_host_free.argtypes = [vp]; L.fastecc_b200_host_free.restype = None
         _lib = L
@@ -174,6 +178,15 @@ def rs_encode_dev(t) -> None:
     _check(lib().fastecc_b200_rs_encode_dev(ptr, N, size, pitch, stream))
 
 
+def rs_encode_dev_timed(t):
+    """One encode with an event between the passes: [(kernel instantiation, ms), ...] (synchronises the stream)."""
+    ptr, N, size, pitch, stream = _dev_args(t)
+    cap = 8
+    ms = (ctypes.c_float * cap)(); names = (ctypes.c_char_p * cap)(); n = ctypes.c_int(cap)
+    _check(lib().fastecc_b200_rs_encode_dev_timed(ptr, N, size, pitch, stream, ms, names, ctypes.byref(n)))
+    return [((names[i] or b"?").decode(), float(ms[i])) for i in range(n.value)]
+
+
 def rs_encode_asym_dev(t, M: int) -> None:
     """Rows [0, M) of t receive the M parity blocks; the other rows are undefined afterwards."""
     ptr, N, size, pitch, stream = _dev_args(t)
@@ -200,11 +213,15 @@ def gfp_to_bytes_dev(words, W: int):
     return raw
 
 
-def reference_hash(data: np.ndarray) -> int:
+def reference_hash(data: Blocks) -> int:
     """main.cpp:203-212 rolling hash over blocks in data[i] order (verification only; sequential by construction)."""
-    a = np.ascontiguousarray(data, dtype=np.uint32).ravel()
-    h = 314159253
-    M32 = 0xFFFFFFFF
-    for v in a.tolist():
-        h = (((h + v) & M32) * 123456791 + (h >> 17)) & M32
-    return h
+    if isinstance(data, np.ndarray):
+        data = np.ascontiguousarray(data, dtype=np.uint32)
+        if data.ndim == 1:
+            data = data.reshape(1, -1)
+        N, SIZE = data.shape
+    else:
+        N, SIZE = len(data), min(int(b.shape[0]) for b in data)
+    tab = (data.ctypes.data + np.arange(N, dtype=np.uint64) * np.uint64(SIZE * 4)) if isinstance(data, np.ndarray) \
+        else np.array([b.ctypes.data for b in data], dtype=np.uint64)
+    return int(lib().fastecc_b200_hash_u32(tab.ctypes.data, N, SIZE))

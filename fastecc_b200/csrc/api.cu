@@ -31,21 +31,48 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
 };
 
+// Stage tables of one plan: built once, on the stream of the first call that needs them.  `ready` is recorded behind the
+// build; a call on any other stream waits for it (a no-op once the build has finished).
+struct TableSet {
+    struct Slot { DevBuf buf; cudaEvent_t ready = nullptr; cudaStream_t built_on = nullptr; };
+    std::vector<Slot> slots;             // one block per pass (plan.h table_bytes)
+};
+// A buffer shared by calls that may come in on different streams (the Y buffer of the two-pass NTT, the repack buffer):
+// `done` is recorded behind its last use and the next user on another stream waits for it, so that two transforms in
+// flight on two streams are serialised on the buffer instead of racing on it.
+struct SharedBuf {
+    DevBuf buf;
+    cudaEvent_t done = nullptr;
+    cudaStream_t last = nullptr;
+    bool used = false;
+    cudaError_t acquire(size_t need, cudaStream_t st) {
+        if (need > buf.bytes && used) { cudaError_t e = cudaEventSynchronize(done); if (e != cudaSuccess) return e; }     // about to be reallocated
+        cudaError_t e = buf.reserve(need);
+        if (e != cudaSuccess) return e;
+        if (!done) { e = cudaEventCreateWithFlags(&done, cudaEventDisableTiming); if (e != cudaSuccess) return e; }
+        if (used && last != st) e = cudaStreamWaitEvent(st, done, 0);
+        return e;
+    }
+    cudaError_t release_to(cudaStream_t st) { used = true; last = st; return cudaEventRecord(done, st); }
+    void destroy() { buf.release(); if (done) cudaEventDestroy(done); done = nullptr; used = false; }
+};
+
 struct Context {
     int device = -1;
     int num_sms = 0;
     uint4* d_tw = nullptr;
-    DevBuf scratch;      // Y buffer of the two-pass NTT
-    DevBuf packed;       // repacked copy for unaligned device layouts
-    DevBuf staging;      // device copy for the host (T**) entry points
-    std::map<uint32_t, std::vector<DevBuf>> tables;   // per (mode, log2 N): one table block per pass (plan.h table_bytes)
+    SharedBuf scratch;   // Y buffer of the two-pass NTT and of the asymmetric encode
+    SharedBuf packed;    // repacked copy for unaligned device layouts
+    DevBuf staging;      // device copy for the host (T**) entry points (serialised by g_mu)
+    std::map<uint32_t, TableSet> tables;              // per (mode, log2 N, ...)
     cudaStream_t stream = nullptr;       // compute
     cudaStream_t h2d = nullptr, d2h = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_done;
 };
 
 Context* g_ctx = nullptr;
-std::mutex g_mu;
+std::mutex g_mu;          // guards g_ctx, the table cache and the shared buffers' bookkeeping (short critical sections)
+std::mutex g_host_mu;     // held by the host (T**) entry points for their whole duration: they share the staging buffer, three streams and the chunk events
 std::atomic<unsigned long long> g_launches{0};
 thread_local char g_err[512] = "no error";
 
@@ -66,8 +93,53 @@ int check_shape(size_t N, size_t size, size_t max_log, const char* who)
     return 0;
 }
 
+// Stage tables of `plan` under cache key `key`: built on first use (into a local set that enters the cache only when every
+// block is allocated and its build launched), then attached to the passes.  which >= 0: only that pass of a 3-pass plan.
+int attach_tables(Context* c, uint32_t key, std::vector<PassParams>& plan, cudaStream_t st, int which = -1, size_t slots = 0)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    TableSet& ts = c->tables[key];
+    const size_t n = slots ? slots : plan.size();
+    if (ts.slots.size() != n) ts.slots.resize(n);
+    for (size_t i = 0; i < plan.size(); ++i) {
+        TableSet::Slot& sl = ts.slots[which >= 0 ? (size_t)which : i];
+        if (!sl.buf.p) {
+            DevBuf nb;
+            cudaEvent_t ev = nullptr;
+            cudaError_t e = nb.reserve(table_bytes(plan[i]));
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = launch_build_tables(plan[i], (uint4*)nb.p, st);
+            if (e == cudaSuccess) e = cudaEventRecord(ev, st);
+            if (e != cudaSuccess) { nb.release(); if (ev) cudaEventDestroy(ev); CUDA_TRY(e); }
+            g_launches++;
+            sl.buf = nb; sl.ready = ev; sl.built_on = st;
+        } else if (sl.built_on != st) {
+            CUDA_TRY(cudaStreamWaitEvent(st, sl.ready, 0));
+        }
+        plan[i].tables = (const uint4*)sl.buf.p;
+        plan[i].table_set_stride = table_sets(plan[i]) > 1 ? (plan[i].nxf << plan[i].log_r) : 0u;
+    }
+    return 0;
+}
+
+struct PassTimer {                       // optional per-pass timing (fastecc_b200_rs_encode_dev_timed)
+    std::vector<cudaEvent_t> ev;
+    std::vector<const char*> names;
+};
+
+int launch_plan(Context* c, std::vector<PassParams>& plan, cudaStream_t st, PassTimer* timer = nullptr)
+{
+    for (size_t i = 0; i < plan.size(); ++i) {
+        const char* name = nullptr;
+        if (timer && i == 0) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); CUDA_TRY(cudaEventRecord(e, st)); timer->ev.push_back(e); }
+        CUDA_TRY(launch_pass(plan[i], c->num_sms, st, &name)); g_launches++;
+        if (timer) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); CUDA_TRY(cudaEventRecord(e, st)); timer->ev.push_back(e); timer->names.push_back(name); }
+    }
+    return 0;
+}
+
 // Run the planned passes on an aligned, padded device buffer.
-int run_aligned(Context* c, uint32_t* x, size_t N, size_t size, size_t pitch, int mode /*0 fwd,1 inv,2 encode*/, cudaStream_t st)
+int run_aligned(Context* c, uint32_t* x, size_t N, size_t size, size_t pitch, int mode /*0 fwd,1 inv,2 encode*/, cudaStream_t st, PassTimer* timer = nullptr)
 {
     const uint32_t pitch4 = (uint32_t)(pitch / 4), s4 = (uint32_t)((size + 3) / 4);
     if (N < ((size_t)1 << kMinLogR)) {
@@ -79,24 +151,16 @@ int run_aligned(Context* c, uint32_t* x, size_t N, size_t size, size_t pitch, in
         return 0;
     }
     Buffers b{x, nullptr, c->d_tw, (uint32_t)pitch, (uint32_t)size};
-    if (mode != 2 && N > ((size_t)1 << kMaxLogR)) {
-        CUDA_TRY(c->scratch.reserve(N * pitch * sizeof(uint32_t)));
-        b.y = (uint32_t*)c->scratch.p;
+    const bool need_y = mode != 2 && N > ((size_t)1 << kMaxLogR);
+    if (need_y) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        CUDA_TRY(c->scratch.acquire(N * pitch * sizeof(uint32_t), st));
+        b.y = (uint32_t*)c->scratch.buf.p;
     }
     std::vector<PassParams> plan = (mode == 2) ? plan_encode(b, N) : plan_ntt(b, N, mode == 1);
-    std::vector<DevBuf>& tabs = c->tables[(uint32_t)mode << 8 | ilog2(N)];
-    if (tabs.empty()) {                                   // first use of this (mode, N): build the per-set stage tables
-        tabs.resize(plan.size());
-        for (size_t i = 0; i < plan.size(); ++i) {
-            CUDA_TRY(tabs[i].reserve(table_bytes(plan[i])));
-            CUDA_TRY(launch_build_tables(plan[i], (uint4*)tabs[i].p, st)); g_launches++;
-        }
-    }
-    for (size_t i = 0; i < plan.size(); ++i) {
-        plan[i].tables = (const uint4*)tabs[i].p;
-        plan[i].table_set_stride = table_sets(plan[i]) > 1 ? (plan[i].nxf << plan[i].log_r) : 0u;
-        CUDA_TRY(launch_pass(plan[i], c->num_sms, st)); g_launches++;
-    }
+    if (int rc = attach_tables(c, (uint32_t)mode << 8 | ilog2(N), plan, st)) return rc;
+    if (int rc = launch_plan(c, plan, st, timer)) return rc;
+    if (need_y) { std::lock_guard<std::mutex> lk(g_mu); CUDA_TRY(c->scratch.release_to(st)); }
     return 0;
 }
 
@@ -105,53 +169,46 @@ int run_aligned_asym(Context* c, uint32_t* x, size_t N, size_t M, size_t size, s
 {
     if (M == N) return run_aligned(c, x, N, size, pitch, 2, st);
     size_t M0 = N;                                        // what the passes produce; M0 >= M
-    if (N > ((size_t)1 << kMaxLogR)) {
+    const bool native = N > ((size_t)1 << kMaxLogR);
+    if (!native) { if (int rc = run_aligned(c, x, N, size, pitch, 2, st)) return rc; }
+    { std::lock_guard<std::mutex> lk(g_mu); CUDA_TRY(c->scratch.acquire(N * pitch * sizeof(uint32_t), st)); }
+    uint32_t* y = (uint32_t*)c->scratch.buf.p;
+    if (native) {
         M0 = M;
         while (!asym_native(N, M0)) M0 *= 2;              // M0 = max(M, N1)
-        CUDA_TRY(c->scratch.reserve(N * pitch * sizeof(uint32_t)));
-        Buffers b{x, (uint32_t*)c->scratch.p, c->d_tw, (uint32_t)pitch, (uint32_t)size};
+        Buffers b{x, y, c->d_tw, (uint32_t)pitch, (uint32_t)size};
         std::vector<PassParams> plan = plan_encode_asym(b, N, M0);
-        std::vector<DevBuf>& tabs = c->tables[0x40000000u | ilog2(N / M0) << 8 | ilog2(N)];
-        if (tabs.empty()) {
-            tabs.resize(plan.size());
-            for (size_t i = 0; i < plan.size(); ++i) {
-                CUDA_TRY(tabs[i].reserve(table_bytes(plan[i])));
-                CUDA_TRY(launch_build_tables(plan[i], (uint4*)tabs[i].p, st)); g_launches++;
-            }
-        }
-        for (size_t i = 0; i < plan.size(); ++i) {
-            plan[i].tables = (const uint4*)tabs[i].p;
-            plan[i].table_set_stride = table_sets(plan[i]) > 1 ? (plan[i].nxf << plan[i].log_r) : 0u;
-            CUDA_TRY(launch_pass(plan[i], c->num_sms, st)); g_launches++;
-        }
-    } else if (int rc = run_aligned(c, x, N, size, pitch, 2, st)) return rc;
-    if (M0 != M) {                                        // keep every (M0/M)-th parity block: gather through the scratch buffer
-        CUDA_TRY(c->scratch.reserve(M * pitch * sizeof(uint32_t)));
-        CUDA_TRY(cudaMemcpy2DAsync(c->scratch.p, pitch * 4, x, (M0 / M) * pitch * 4, size * 4, M, cudaMemcpyDeviceToDevice, st));
-        CUDA_TRY(cudaMemcpy2DAsync(x, pitch * 4, c->scratch.p, pitch * 4, size * 4, M, cudaMemcpyDeviceToDevice, st));
+        if (int rc = attach_tables(c, 0x40000000u | ilog2(N / M0) << 8 | ilog2(N), plan, st)) return rc;
+        if (int rc = launch_plan(c, plan, st)) return rc;
     }
+    if (M0 != M) {                                        // keep every (M0/M)-th parity block: gather through the scratch buffer
+        CUDA_TRY(cudaMemcpy2DAsync(y, pitch * 4, x, (M0 / M) * pitch * 4, size * 4, M, cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(cudaMemcpy2DAsync(x, pitch * 4, y, pitch * 4, size * 4, M, cudaMemcpyDeviceToDevice, st));
+    }
+    { std::lock_guard<std::mutex> lk(g_mu); CUDA_TRY(c->scratch.release_to(st)); }
     return 0;
 }
 
-int run_dev(uint32_t* d, size_t N, size_t size, size_t pitch, int mode, void* stream, const char* who)
+int run_dev(uint32_t* d, size_t N, size_t size, size_t pitch, int mode, void* stream, const char* who, PassTimer* timer = nullptr)
 {
     Context* c = g_ctx;
     if (!c) return fail(FASTECC_B200_ENOINIT, "%s: call fastecc_b200_init() first", who);
     if (!d) return fail(FASTECC_B200_EINVAL, "%s: null device pointer", who);
     if (int rc = check_shape(N, size, mode == 2 ? FASTECC_B200_MAX_LOG_N_ENCODE : FASTECC_B200_MAX_LOG_N, who)) return rc;
-    if (pitch < size) return fail(FASTECC_B200_EINVAL, "%s: pitch_words (%zu) < SIZE_words (%zu)", who, pitch, size);
+    if (pitch < size || pitch > 0xFFFFFFF0u) return fail(FASTECC_B200_EINVAL, "%s: pitch_words (%zu) must be in [SIZE_words (%zu), 2^32 - 16]", who, pitch, size);
     if ((unsigned long long)N * ((pitch + 3) / 4) >= (1ull << 32))
         return fail(FASTECC_B200_EINVAL, "%s: buffer of %zu x %zu words is 64 GiB or more (32-bit chunk indexing)", who, N, pitch);
     cudaStream_t st = (cudaStream_t)stream;
     const bool aligned = (pitch % 4 == 0) && (((uintptr_t)d) % 16 == 0);
-    if (aligned) return run_aligned(c, d, N, size, pitch, mode, st);
+    if (aligned) return run_aligned(c, d, N, size, pitch, mode, st, timer);
     // unaligned layout: repack into a padded copy, transform, copy the SIZE data words back
     const size_t ppitch = (size + 3) / 4 * 4;
-    CUDA_TRY(c->packed.reserve(N * ppitch * sizeof(uint32_t)));
-    uint32_t* pk = (uint32_t*)c->packed.p;
+    { std::lock_guard<std::mutex> lk(g_mu); CUDA_TRY(c->packed.acquire(N * ppitch * sizeof(uint32_t), st)); }
+    uint32_t* pk = (uint32_t*)c->packed.buf.p;
     CUDA_TRY(launch_pack(d, pitch, pk, ppitch, N, (uint32_t)size, st)); g_launches++;
-    if (int rc = run_aligned(c, pk, N, size, ppitch, mode, st)) return rc;
+    if (int rc = run_aligned(c, pk, N, size, ppitch, mode, st, timer)) return rc;
     CUDA_TRY(launch_unpack(pk, ppitch, d, pitch, N, (uint32_t)size, st)); g_launches++;
+    { std::lock_guard<std::mutex> lk(g_mu); CUDA_TRY(c->packed.release_to(st)); }
     return 0;
 }
 
@@ -162,6 +219,7 @@ int run_host(uint32_t** data, size_t N, size_t size, int mode, const char* who)
     if (!data) return fail(FASTECC_B200_EINVAL, "%s: null block table", who);
     if (int rc = check_shape(N, size, mode == 2 ? FASTECC_B200_MAX_LOG_N_ENCODE : FASTECC_B200_MAX_LOG_N, who)) return rc;
     for (size_t i = 0; i < N; i++) if (!data[i]) return fail(FASTECC_B200_EINVAL, "%s: data[%zu] is null", who, i);
+    std::lock_guard<std::mutex> host_lock(g_host_mu);
     const size_t pitch = (size + 3) / 4 * 4;
     CUDA_TRY(c->staging.reserve(N * pitch * sizeof(uint32_t)));
     uint32_t* dv = (uint32_t*)c->staging.p;
@@ -242,8 +300,8 @@ void fastecc_b200_shutdown(void)
     if (!g_ctx) return;
     cudaSetDevice(g_ctx->device);
     cudaDeviceSynchronize();
-    g_ctx->scratch.release(); g_ctx->packed.release(); g_ctx->staging.release();
-    for (auto& kv : g_ctx->tables) for (auto& b : kv.second) b.release();
+    g_ctx->scratch.destroy(); g_ctx->packed.destroy(); g_ctx->staging.release();
+    for (auto& kv : g_ctx->tables) for (auto& sl : kv.second.slots) { sl.buf.release(); if (sl.ready) cudaEventDestroy(sl.ready); }
     if (g_ctx->d_tw) cudaFree(g_ctx->d_tw);
     if (g_ctx->stream) cudaStreamDestroy(g_ctx->stream);
     if (g_ctx->h2d) cudaStreamDestroy(g_ctx->h2d);
@@ -264,6 +322,40 @@ int fastecc_b200_ntt_u32_dev(uint32_t* d, size_t N, size_t size, size_t pitch, i
 int fastecc_b200_rs_encode_dev(uint32_t* d, size_t N, size_t size, size_t pitch, void* stream)
 { return run_dev(d, N, size, pitch, 2, stream, "fastecc_b200_rs_encode_dev"); }
 
+int fastecc_b200_rs_encode_dev_timed(uint32_t* d, size_t N, size_t size, size_t pitch, void* stream, float* pass_ms, const char** pass_kernel, int* n_passes)
+{
+    const char* who = "fastecc_b200_rs_encode_dev_timed";
+    if (!pass_ms || !n_passes || *n_passes < 1) return fail(FASTECC_B200_EINVAL, "%s: pass_ms / n_passes missing", who);
+    PassTimer t;
+    int rc = run_dev(d, N, size, pitch, 2, stream, who, &t);
+    if (rc == 0 && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) rc = fail(FASTECC_B200_ECUDA, "%s: %s", who, cudaGetErrorString(cudaGetLastError()));
+    int n = 0;
+    for (size_t i = 0; rc == 0 && i + 1 < t.ev.size() && n < *n_passes; ++i, ++n) {
+        if (cudaEventElapsedTime(&pass_ms[n], t.ev[i], t.ev[i + 1]) != cudaSuccess) rc = fail(FASTECC_B200_ECUDA, "%s: cudaEventElapsedTime failed", who);
+        if (pass_kernel) pass_kernel[n] = t.names[i];
+    }
+    for (cudaEvent_t e : t.ev) cudaEventDestroy(e);
+    *n_passes = n;
+    return rc;
+}
+
+int fastecc_b200_shard_geometry(size_t N, int n_ranks, size_t* N1, size_t* N2, int* fused_exchange_ok)
+{
+    if (!is_pow2(N) || N < 2) return fail(FASTECC_B200_EINVAL, "fastecc_b200_shard_geometry: N must be a power of two");
+    const uint32_t LN = ilog2(N), L1 = LN <= (uint32_t)kMaxLogR ? LN : split_l1(LN);
+    if (N1) *N1 = (size_t)1 << L1;
+    if (N2) *N2 = (size_t)1 << (LN - L1);
+    if (fused_exchange_ok) *fused_exchange_ok = n_ranks >= 2 && shard_p2p_supported(N, (uint32_t)n_ranks) ? 1 : 0;
+    return n_ranks < 2 || shard_supported(N, (uint32_t)n_ranks) ? 0 : fail(FASTECC_B200_EINVAL, "fastecc_b200_shard_geometry: N=%zu cannot be sharded over %d ranks", N, n_ranks);
+}
+
+int fastecc_b200_copy2d_async(void* dst, size_t dst_pitch_bytes, const void* src, size_t src_pitch_bytes, size_t width_bytes, size_t rows, int to_device, void* stream)
+{
+    if (!g_ctx) return fail(FASTECC_B200_ENOINIT, "fastecc_b200_copy2d_async: call fastecc_b200_init() first");
+    CUDA_TRY(cudaMemcpy2DAsync(dst, dst_pitch_bytes, src, src_pitch_bytes, width_bytes, rows, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return 0;
+}
+
 int fastecc_b200_gf_mul_dev(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, void* stream)
 {
     if (!g_ctx) return fail(FASTECC_B200_ENOINIT, "fastecc_b200_gf_mul_dev: call fastecc_b200_init() first");
@@ -283,8 +375,7 @@ int fastecc_b200_row_scale_dev(uint32_t* d, size_t n_rows, size_t size, size_t p
     const char* who = "fastecc_b200_row_scale_dev";
     if (!g_ctx) return fail(FASTECC_B200_ENOINIT, "%s: call fastecc_b200_init() first", who);
     if (!d || !d_consts) return fail(FASTECC_B200_EINVAL, "%s: null device pointer", who);
-    if (size == 0 || pitch < size || pitch % 4 || ((uintptr_t)d) % 16) return fail(FASTECC_B200_EINVAL, "%s: needs SIZE >= 1, pitch_words >= SIZE, pitch %% 4 == 0 and a 16-byte aligned buffer (pad words of a row are scaled too)", who);
-    if (pitch / 4 >= (1ull << 32)) return fail(FASTECC_B200_EINVAL, "%s: rows too long", who);
+    if (size == 0 || pitch < size || pitch > 0xFFFFFFF0u || pitch % 4 || ((uintptr_t)d) % 16) return fail(FASTECC_B200_EINVAL, "%s: needs SIZE >= 1, SIZE <= pitch_words <= 2^32 - 16, pitch %% 4 == 0 and a 16-byte aligned buffer (pad words of a row are scaled too)", who);
     CUDA_TRY(launch_row_scale(d, n_rows, (uint32_t)((size + 3) / 4), (uint32_t)(pitch / 4), d_consts, g_ctx->num_sms, (cudaStream_t)stream)); g_launches++;
     return 0;
 }
@@ -320,7 +411,7 @@ int fastecc_b200_rs_encode_asym_dev(uint32_t* d, size_t N, size_t M, size_t size
     if (!d) return fail(FASTECC_B200_EINVAL, "%s: null device pointer", who);
     if (int rc = check_shape(N, size, FASTECC_B200_MAX_LOG_N_ENCODE, who)) return rc;
     if (!is_pow2(M) || M > N) return fail(FASTECC_B200_EINVAL, "%s: M=%zu must be a power of two in [1, N]", who, M);
-    if (pitch < size || pitch % 4 || ((uintptr_t)d) % 16) return fail(FASTECC_B200_EINVAL, "%s: needs pitch_words >= SIZE_words, pitch %% 4 == 0 and a 16-byte aligned buffer", who);
+    if (pitch < size || pitch > 0xFFFFFFF0u || pitch % 4 || ((uintptr_t)d) % 16) return fail(FASTECC_B200_EINVAL, "%s: needs SIZE_words <= pitch_words <= 2^32 - 16, pitch %% 4 == 0 and a 16-byte aligned buffer", who);
     if ((unsigned long long)N * (pitch / 4) >= (1ull << 32)) return fail(FASTECC_B200_EINVAL, "%s: buffer too large (32-bit chunk indexing)", who);
     return run_aligned_asym(c, d, N, M, size, pitch, (cudaStream_t)stream);
 }
@@ -334,6 +425,7 @@ int fastecc_b200_rs_encode_asym(uint32_t** data, size_t N, size_t M, size_t size
     if (int rc = check_shape(N, size, FASTECC_B200_MAX_LOG_N_ENCODE, who)) return rc;
     if (!is_pow2(M) || M > N) return fail(FASTECC_B200_EINVAL, "%s: M=%zu must be a power of two in [1, N]", who, M);
     for (size_t i = 0; i < N; i++) if (!data[i]) return fail(FASTECC_B200_EINVAL, "%s: data[%zu] is null", who, i);
+    std::lock_guard<std::mutex> host_lock(g_host_mu);
     const size_t pitch = (size + 3) / 4 * 4;
     CUDA_TRY(c->staging.reserve(N * pitch * sizeof(uint32_t)));
     uint32_t* dv = (uint32_t*)c->staging.p;
@@ -357,20 +449,14 @@ int fastecc_b200_rs_encode_shard_pass(uint32_t* d_local, size_t N, int n_ranks, 
     if (!c) return fail(FASTECC_B200_ENOINIT, "%s: call fastecc_b200_init() first", who);
     if (!d_local || which < 0 || which > 2 || rank < 0 || rank >= n_ranks) return fail(FASTECC_B200_EINVAL, "%s: bad arguments", who);
     if (!shard_supported(N, (uint32_t)n_ranks)) return fail(FASTECC_B200_EINVAL, "%s: N=%zu cannot be sharded over %d ranks (need a power of two 2^11..2^19 with N2 %% ranks == 0)", who, N, n_ranks);
-    if (size == 0 || pitch < size || pitch % 4 || ((uintptr_t)d_local) % 16) return fail(FASTECC_B200_EINVAL, "%s: needs SIZE >= 1, a 16-byte aligned buffer and pitch %% 4 == 0", who);
+    if (size == 0 || pitch < size || pitch > 0xFFFFFFF0u || pitch % 4 || ((uintptr_t)d_local) % 16) return fail(FASTECC_B200_EINVAL, "%s: needs SIZE >= 1, a 16-byte aligned buffer and pitch %% 4 == 0", who);
     if ((unsigned long long)(N / n_ranks) * (pitch / 4) >= (1ull << 32)) return fail(FASTECC_B200_EINVAL, "%s: local buffer too large", who);
     cudaStream_t st = (cudaStream_t)stream;
     Buffers b{d_local, nullptr, c->d_tw, (uint32_t)pitch, (uint32_t)size};
     PassParams p = plan_encode_shard(b, N, (uint32_t)n_ranks, (uint32_t)rank, which);
-    std::vector<DevBuf>& tabs = c->tables[0x80000000u | (uint32_t)n_ranks << 16 | (uint32_t)rank << 8 | ilog2(N)];
-    if (tabs.empty()) tabs.resize(3);
-    if (!tabs[which].p) {
-        CUDA_TRY(tabs[which].reserve(table_bytes(p)));
-        CUDA_TRY(launch_build_tables(p, (uint4*)tabs[which].p, st)); g_launches++;
-    }
-    p.tables = (const uint4*)tabs[which].p;
-    p.table_set_stride = table_sets(p) > 1 ? (p.nxf << p.log_r) : 0u;
-    CUDA_TRY(launch_pass(p, c->num_sms, st)); g_launches++;
+    std::vector<PassParams> one{p};
+    if (int rc = attach_tables(c, 0x80000000u | (uint32_t)n_ranks << 16 | (uint32_t)rank << 8 | ilog2(N), one, st, which, 3)) return rc;
+    CUDA_TRY(launch_pass(one[0], c->num_sms, st)); g_launches++;
     return 0;
 }
 
@@ -383,21 +469,15 @@ int fastecc_b200_rs_encode_shard_pass_p2p(const uint32_t* d_src, uint32_t* const
     if (!d_src || !d_peers || which < 0 || which > 2 || rank < 0 || rank >= n_ranks) return fail(FASTECC_B200_EINVAL, "%s: bad arguments", who);
     if (!shard_p2p_supported(N, (uint32_t)n_ranks))
         return fail(FASTECC_B200_EINVAL, "%s: N=%zu cannot be sharded over %d ranks with fused exchange (need 2^11..2^19, ranks <= 8 and <= both tile heights / 32)", who, N, n_ranks);
-    if (size == 0 || pitch < size || pitch % 4 || ((uintptr_t)d_src) % 16) return fail(FASTECC_B200_EINVAL, "%s: needs SIZE >= 1, 16-byte aligned buffers and pitch %% 4 == 0", who);
+    if (size == 0 || pitch < size || pitch > 0xFFFFFFF0u || pitch % 4 || ((uintptr_t)d_src) % 16) return fail(FASTECC_B200_EINVAL, "%s: needs SIZE >= 1, 16-byte aligned buffers and pitch %% 4 == 0", who);
     for (int r = 0; r < n_ranks; ++r)
         if (!d_peers[r] || ((uintptr_t)d_peers[r]) % 16) return fail(FASTECC_B200_EINVAL, "%s: peer buffer %d missing or misaligned", who, r);
     if ((unsigned long long)(N / n_ranks) * (pitch / 4) >= (1ull << 32)) return fail(FASTECC_B200_EINVAL, "%s: local buffer too large", who);
     cudaStream_t st = (cudaStream_t)stream;
     PassParams p = plan_encode_shard_p2p(d_src, d_peers, c->d_tw, (uint32_t)pitch, (uint32_t)size, N, (uint32_t)n_ranks, (uint32_t)rank, which);
-    std::vector<DevBuf>& tabs = c->tables[0x80000000u | (uint32_t)n_ranks << 16 | (uint32_t)rank << 8 | ilog2(N)];
-    if (tabs.empty()) tabs.resize(3);
-    if (!tabs[which].p) {
-        CUDA_TRY(tabs[which].reserve(table_bytes(p)));
-        CUDA_TRY(launch_build_tables(p, (uint4*)tabs[which].p, st)); g_launches++;
-    }
-    p.tables = (const uint4*)tabs[which].p;
-    p.table_set_stride = table_sets(p) > 1 ? (p.nxf << p.log_r) : 0u;
-    CUDA_TRY(launch_pass(p, c->num_sms, st)); g_launches++;
+    std::vector<PassParams> one{p};
+    if (int rc = attach_tables(c, 0x80000000u | (uint32_t)n_ranks << 16 | (uint32_t)rank << 8 | ilog2(N), one, st, which, 3)) return rc;
+    CUDA_TRY(launch_pass(one[0], c->num_sms, st)); g_launches++;
     return 0;
 }
 
@@ -438,6 +518,16 @@ int fastecc_b200_ntt_u32(uint32_t** data, size_t N, size_t size, int inverse)
 
 int fastecc_b200_rs_encode(uint32_t** data, size_t N, size_t size)
 { return run_host(data, N, size, 2, "fastecc_b200_rs_encode"); }
+
+uint32_t fastecc_b200_hash_u32(uint32_t* const* data, size_t N, size_t size)
+{
+    uint32_t h = 314159253u;
+    for (size_t i = 0; i < N; i++) {
+        const uint32_t* p = data[i];
+        for (size_t k = 0; k < size; k++) h = (h + p[k]) * 123456791u + (h >> 17);
+    }
+    return h;
+}
 
 void* fastecc_b200_host_alloc(size_t bytes)
 {

@@ -9,7 +9,9 @@
 //      v = lo32(b*w) - lo32(q*P) = b*w + q*(2^32-P)   (mod 2^32)         (2 x IMAD)
 // q equals floor(b*w/P) exactly unless b*w is a multiple of P, in which case it may be one less; so
 //      v == b*w mod P   with v in [0, P]          for ANY 32-bit b  (b need not be reduced).
-// No conditional subtract.  Values between butterflies are kept "lazy" in [0, 2^32) (congruent mod P):
+// No conditional subtract.  That form (mul) serves the element-wise kernels and the small-order DFT.  The pass kernels use
+// mul_h, which takes the quotient from the FP64 unit instead of two IMAD.HI (see below and DESIGN.md section 4).
+// Values between butterflies are kept "lazy" in [0, 2^32) (congruent mod P):
 //      addl(a, v):  a in [0,2^32), v in [0,P]  ->  a+v mod P  in [0,2^32)     (add, then +(2^32-P) on carry)
 //      subl(a, v):  a in [0,2^32), v in [0,P]  ->  a-v mod P  in [0,2^32)     (sub, then -(2^32-P) on borrow)
 // which are closed (proof in DESIGN.md section 4); canon() maps a lazy value to the canonical residue [0,P).
@@ -32,7 +34,7 @@ constexpr uint32_t GEN = 19;                  // generator used by GF_Root (GF(p
 constexpr uint32_t LOG_M = 20;                // largest power-of-two order: P-1 = 2^20 * 4095
 constexpr uint32_t M = 1u << LOG_M;
 
-struct Tw { uint32_t w, whi, wlo, wm; };      // one twiddle: w, floor(w*2^64/P), and w*2^32 mod P (Montgomery form); 16 bytes
+struct Tw { uint32_t w, whi, wlo, pad; };     // one entry of the global power table: w and W = floor(w*2^64/P); 16 bytes
 
 // `zero` must be a register holding 0 that the compiler cannot constant-fold (see opaque_zero()): it becomes the
 // high half of the 64-bit addend of the second IMAD.HI, which saves ptxas from re-materialising a zero register
@@ -51,27 +53,59 @@ GF_HD uint32_t mul(uint32_t b, uint32_t w, uint32_t whi, uint32_t wlo, uint32_t 
     return q * C + b * w;
 }
 
-// The same product through a Montgomery reduction (R = 2^32): wm = w*2^32 mod P.  P^-1 mod 2^32 = 1 + 2^20, so the
-// reduction factor m = lo*(1 + 2^20) is one LEA on the ALU pipe; T - m*P is divisible by 2^32 and
-// (T - m*P)/2^32 = hi(T) - hi(m*P) lies in (-P, P).  IMAD.WIDE + IMAD.HI + 3 ALU instructions: fewer cycles on the
-// integer-multiply pipe than mul() (2 x IMAD.HI + 2 x IMAD), more on the ALU pipe -- the kernels use mul() for one
-// word of a pair and mul_mont() for the other to load both pipes evenly.  Result in [0, P).
-GF_HD uint32_t mul_mont(uint32_t b, uint32_t wm)
+// ---- the product of the pass kernels: quotient on the FP64 unit ----------------------------------------------------
+// A B200 issues IMAD.HI at half the IMAD rate (4.7 vs 2.1 cycles per warp instruction and scheduler, tools/ubench2.cu),
+// so the two IMAD.HI of mul() are 2/3 of its multiplier time.  mul_h gets the quotient from one DFMA instead:
+//      wp = RD53(W * 2^-64) <= w/P                          (53-bit truncation of the same W; stage tables hold it)
+//      q  = lo32( fma.rm( double(b), wp, 2^52 ) ) = floor(b * wp)         exactly: one rounding, towards -inf, at ulp 1
+//      v  = b*w + q*(2^32-P)  (mod 2^32)                                   2 x IMAD
+// 0 <= b*(w/P - wp) < 2^32 * (2^-53 + 2^-64), so q is floor(b*w/P) or, only when (b*w mod P) <= 2^11, one less:
+// v = b*w - q*P lies in [0, P + 2^11] and fits 32 bits; one VIADDMNMX (min(v, v-P) unsigned) brings it into [0, P).
+// double(b) is an exact I2F.F64.U32.  Valid for ANY 32-bit b, like mul().  Validated on a B200 against 64-bit
+// arithmetic on 4M operand pairs incl. 1.4M adversarial ones with b*w mod P < 5000 (profiles/r02_ubench2_fp64_quotient.log).
+//
+// wp_bits: the IEEE-754 encoding {lo, hi} of wp, built with integer operations only so that host and device agree.
+GF_HD uint32_t clz64(uint64_t x)
 {
-    const uint64_t T = (uint64_t)b * wm;
-    const uint32_t lo = (uint32_t)T, hi = (uint32_t)(T >> 32);
-    const uint32_t m = lo + (lo << 20);
 #if defined(__CUDA_ARCH__)
-    const uint32_t h2 = __umulhi(m, P);
-    uint32_t r;
-    asm("{\n\t.reg .pred q;\n\t.reg .u32 c;\n\tsub.cc.u32 %0, %1, %2;\n\taddc.u32 c, 0, 0;\n\tsetp.eq.u32 q, c, 0;\n\t@q add.u32 %0, %0, 0xFFF00001;\n\t}"
-        : "=r"(r) : "r"(hi), "r"(h2));
-    return r;
+    return (uint32_t)__clzll((long long)x);
 #else
-    const uint32_t h2 = (uint32_t)(((uint64_t)m * P) >> 32);
-    const uint32_t r = hi - h2;
-    return hi < h2 ? r + P : r;
+    return (uint32_t)__builtin_clzll(x);
 #endif
+}
+GF_HD void wp_bits(uint32_t whi, uint32_t wlo, uint32_t& lo, uint32_t& hi)
+{
+    const uint64_t W = ((uint64_t)whi << 32) | wlo;
+    if (!W) { lo = 0; hi = 0; return; }
+    const uint32_t lz = clz64(W);
+    const uint64_t m = W << lz;                                   // bit 63 set:  W*2^-64 = (m / 2^63) * 2^(-1-lz)
+    const uint64_t bits = ((uint64_t)(1022u - lz) << 52) | ((m >> 11) & ((1ull << 52) - 1));      // truncation = round down
+    lo = (uint32_t)bits; hi = (uint32_t)(bits >> 32);
+}
+GF_HD uint32_t mul_h(uint32_t b, uint32_t w, uint32_t wplo, uint32_t wphi)
+{
+    uint32_t q;
+#if defined(__CUDA_ARCH__)
+    double bd, qd;
+    const double wp = __hiloint2double((int)wphi, (int)wplo);
+#if defined(FECC_CVT_MAGIC)      // experiment: {b, 0x43300000} - 2^52 on the FP64 unit instead of I2F on the XU pipe
+    asm("{\n\t.reg .f64 t;\n\tmov.b64 t, {%1, %2};\n\tsub.rn.f64 %0, t, 0d4330000000000000;\n\t}" : "=d"(bd) : "r"(b), "r"(0x43300000u));
+#else
+    asm("cvt.rn.f64.u32 %0, %1;" : "=d"(bd) : "r"(b));
+#endif
+    asm("fma.rm.f64 %0, %1, %2, 0d4330000000000000;" : "=d"(qd) : "d"(bd), "d"(wp));
+    q = (uint32_t)__double2loint(qd);
+#else
+    q = 0;                                                        // floor(b * wp) in integers: wp = mant * 2^(e-52)
+    const uint64_t bits = ((uint64_t)wphi << 32) | wplo;
+    if (bits) {
+        const uint64_t mant = (bits & ((1ull << 52) - 1)) | (1ull << 52);
+        const int sh = 52 - ((int)(bits >> 52) - 1023);           // >= 53 because wp < 1
+        if (sh < 128) q = (uint32_t)(((unsigned __int128)b * mant) >> sh);
+    }
+#endif
+    const uint32_t v = q * C + b * w, t = v - P;
+    return v < t ? v : t;
 }
 
 GF_HD uint32_t addl(uint32_t a, uint32_t v)
@@ -121,7 +155,7 @@ inline Tw make_tw(uint32_t w)            // {w, floor(w*2^64/P)} by two 64/32 lo
     const uint64_t n1 = (uint64_t)w << 32;
     const uint64_t whi = n1 / P, rem = n1 % P;
     const uint64_t wlo = (rem << 32) / P;
-    Tw t; t.w = w; t.whi = (uint32_t)whi; t.wlo = (uint32_t)wlo; t.wm = (uint32_t)(n1 % P); return t;
+    Tw t; t.w = w; t.whi = (uint32_t)whi; t.wlo = (uint32_t)wlo; t.pad = 0; return t;
 }
 
 } // namespace gf

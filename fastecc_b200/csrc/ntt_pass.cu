@@ -14,11 +14,11 @@
 //   * 64-bit stores of the finished rows straight from registers.
 // The kernel is bound by the integer multiply pipe (IMAD.HI on "fmaheavy"), not by HBM: see profiles/.
 #include "ntt_tile.cuh"
-#include "ntt_warp.cuh"
 #include "ntt_pass.h"
 #include "plan.h"
 #include <cstring>
 #include <cstdlib>
+#include <cstdio>
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -49,14 +49,6 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-// L2 prefetch of a tensor box (no shared-memory destination): used to pull a work item's whole column block
-// (strips_per_item strips wide, i.e. >= 256 contiguous bytes per row) into L2 a few tiles before its 64-byte-wide
-// tiles are requested -- the strided passes touch a different DRAM page per row, and 64-byte accesses waste most of
-// each page activation.
-__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, uint32_t c0, uint32_t c1, uint32_t c2)
-{
-    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" :: "l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -79,8 +71,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarr
 // LR / NXF / TMA are compile-time: the kernel patches them into its copy of the parameters, so every shift, stride
 // and placement branch in ntt_tile.cuh folds to an immediate (keeps the 64 data registers from spilling).
 template <int LR, int NXF, int TMA>
-__global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(const PassParams Pin, const __grid_constant__ CUtensorMap tmap,
-                                                               const __grid_constant__ CUtensorMap pf_map)
+__global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(const PassParams Pin, const __grid_constant__ CUtensorMap tmap)
 {
     PassParams P = Pin;
     P.log_r = LR; P.nxf = NXF; P.use_tma = TMA != 0;
@@ -96,7 +87,6 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(const PassParams 
     const uint32_t nslots = var1 ? 4u : (var0 ? (uint32_t)NXF + 1u : (uint32_t)NXF);
     uint64_t* bar = reinterpret_cast<uint64_t*>(tabs + nslots * R);
     const uint32_t tid  = threadIdx.x;
-    const uint32_t zero = gf::opaque_zero();
     const uint32_t groups = (P.nstrips + P.strips_per_item - 1) / P.strips_per_item;
     const uint32_t nitems = P.nsets * groups;
     constexpr uint32_t nsteps = NXF == 2 ? (LR > kStages ? 3u : 1u) : (LR > kStages ? 2u : 1u);
@@ -125,14 +115,6 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(const PassParams 
                 const uint32_t tbv = first ? 0u : tbuf;
                 if (ld0) bulk_load(tabs + ((var0 ? tbv : 0u) * NXF + 0) * R, tsrc, R * 16u, bar);
                 if (ld1) bulk_load(tabs + ((var1 ? tbv : 0u) * NXF + 1) * R, tsrc + R, R * 16u, bar);
-                if (P.l2_prefetch && strip % P.strips_per_item == 0) {                  // first tile of an item: pull the NEXT item into L2
-                    const uint32_t item = set * groups + strip / P.strips_per_item + gridDim.x;
-                    if (item < nitems) {
-                        const uint32_t ps = item / groups, pstrip = (item - ps * groups) * P.strips_per_item;
-#pragma unroll
-                        for (uint32_t b = 0; b < kBoxes; ++b) tma_prefetch_3d(&pf_map, pstrip * kWt, b * kRowsBox, ps);
-                    }
-                }
             }
         } else {
             load_tile_cpasync(P, set, strip, tid, tile);
@@ -179,7 +161,9 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(const PassParams 
             }
             const uint4* tw0 = tabs + ((var0 ? tb : 0u) * NXF) * R;
             const uint4* tw1 = tabs + ((var1 ? tb : 0u) * NXF + 1) * R;
-            if (active && !P.debug_skip_math) round_math(P, st, tid, cur_set, tw0, tw1, r, zero);
+            #if !defined(FECC_SKIP_MATH)                                   // -DFECC_SKIP_MATH: copy-only build for measuring the memory floor of a pass
+            if (active) round_math(P, st, tid, cur_set, tw0, tw1, r);
+#endif
             if (!last) {
                 if (active) round_write_tile(P, st.k, st.xfi == 0, tid, tile, r);
                 __syncthreads();
@@ -225,7 +209,6 @@ __global__ void __launch_bounds__(2 * kThreads, 1) ntt_pass_dual_kernel(const Pa
     uint64_t* rbar  = full + 2 * kBufs;                                         // rbar[2]: the group's 8 warps are done reading their tile
     uint64_t* tfull = rbar + 2;                                                 // tfull[2]: the group's next table has landed ([0] also: the shared table)
     const uint32_t g = threadIdx.x / kThreads, tid = threadIdx.x % kThreads;
-    const uint32_t zero = gf::opaque_zero();
     const uint32_t groups = (P.nstrips + P.strips_per_item - 1) / P.strips_per_item;
     const uint32_t nitems = P.nsets * groups;
     constexpr uint32_t nsteps = LR > kStages ? 2u : 1u;
@@ -292,7 +275,9 @@ __global__ void __launch_bounds__(2 * kThreads, 1) ntt_pass_dual_kernel(const Pa
                     if (var0) request_table(k + 2, 2 * g + ((j + 1) & 1u), tfull + g);   // our own next table: its slot was last used by tile k-2
                 }
             }
-            if (active && !P.debug_skip_math) round_math(P, st, tid, cur_set, tw0, tw0, r, zero);
+            #if !defined(FECC_SKIP_MATH)
+            if (active) round_math(P, st, tid, cur_set, tw0, tw0, r);
+#endif
             if (!last) {
                 if (active) round_write_tile(P, st.k, true, tid, tile, r);
                 group_sync(g);
@@ -305,139 +290,6 @@ __global__ void __launch_bounds__(2 * kThreads, 1) ntt_pass_dual_kernel(const Pa
     }
 }
 
-__device__ __forceinline__ void tma_store_3d(const void* src, const CUtensorMap* map, uint32_t c0, uint32_t c1, uint32_t c2)
-{
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                 :: "l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void bulk_commit()        { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all()      { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
-// Warp-private schedule (ntt_warp.cuh): TMA in, eight independent warps, TMA out, one CTA per SM with TWO tile buffers.
-// No block barrier in the tile loop: a tile's arrival is an mbarrier wait; the last warp to finish a tile (shared
-// counter) writes it back with cp.async.bulk.tensor stores and, once the store has read the buffer, requests the tile
-// after next into it -- which then has a whole tile's worth of butterflies to land.
-template <int LR, int NXF>
-__global__ void __launch_bounds__(kThreads, 1) ntt_pass_warp_kernel(const PassParams Pin, const __grid_constant__ CUtensorMap src_map,
-                                                                    const __grid_constant__ CUtensorMap dst_map, const __grid_constant__ CUtensorMap pf_map)
-{
-    PassParams P = Pin;
-    P.log_r = LR; P.nxf = NXF;
-    extern __shared__ __align__(1024) uint4 smem[];
-    constexpr uint32_t R = 1u << LR;
-    uint4* tabs = smem + 2 * kTileChunks;                 // [2 buffers][NXF][R]
-    uint64_t* bar = reinterpret_cast<uint64_t*>(tabs + 2 * NXF * R);      // full[2]
-    uint32_t* done = reinterpret_cast<uint32_t*>(bar + 2);                // done[2]
-    const uint32_t tid = threadIdx.x, lane = tid & 31u;
-    const uint32_t zero = gf::opaque_zero();
-    const uint32_t groups = (P.nstrips + P.strips_per_item - 1) / P.strips_per_item;
-    const uint32_t nitems = P.nsets * groups;
-    constexpr uint32_t kWt = 16384u >> LR;                // words per tile row
-    constexpr uint32_t kWb = kWt < 32u ? kWt : 32u;       // words per row of a column block (TMA box inner extent)
-    constexpr uint32_t kColBlocks = kWt / kWb;
-    constexpr uint32_t kRowsBox = R < 256u ? R : 256u;
-    constexpr uint32_t kRowBoxes = R / kRowsBox;
-    constexpr uint32_t kTableBytes = NXF * R * 16u;
-    const WarpPos wp = warp_pos(LR, tid);
-    const WarpAddr wa = warp_addr(LR, wp);
-
-    uint32_t cur_set, cur_strip;
-    if (!tile_decode(P, groups, nitems, 0, cur_set, cur_strip)) return;
-
-    auto box_ptr = [&](uint32_t buf, uint32_t cb, uint32_t rb) { return smem + buf * kTileChunks + cb * (R * (kWb / 4)) + rb * (kRowsBox * (kWb / 4)); };
-    auto request = [&](uint32_t buf, uint32_t set, uint32_t strip, bool with_tables, uint32_t tbuf) {      // one thread
-        fence_proxy_async();
-        mbar_expect_tx(bar + buf, kTileBytes + (with_tables ? kTableBytes : 0u));
-#pragma unroll
-        for (uint32_t cb = 0; cb < kColBlocks; ++cb)
-#pragma unroll
-            for (uint32_t rb = 0; rb < kRowBoxes; ++rb)
-                tma_load_3d(box_ptr(buf, cb, rb), &src_map, bar + buf, strip * kWt + cb * kWb, rb * kRowsBox, set);
-        if (with_tables) bulk_load(tabs + tbuf * NXF * R, P.tables + (size_t)set * P.table_set_stride, kTableBytes, bar + buf);
-        if (P.l2_prefetch && strip % P.strips_per_item == 0) {                          // first tile of an item: pull the NEXT item into L2
-            const uint32_t item = set * groups + strip / P.strips_per_item + gridDim.x;
-            if (item < nitems) {
-                const uint32_t ps = item / groups, pstrip = (item - ps * groups) * P.strips_per_item;
-#pragma unroll
-                for (uint32_t rb = 0; rb < kRowBoxes; ++rb) tma_prefetch_3d(&pf_map, pstrip * kWt, rb * kRowsBox, ps);
-            }
-        }
-    };
-
-    if (tid == 0) {
-        mbar_init(bar, 1); mbar_init(bar + 1, 1); done[0] = 0; done[1] = 0; fence_mbar_init();
-    }
-    __syncthreads();
-    if (tid == 0) {                                       // prologue: tiles 0 and 1
-        request(0, cur_set, cur_strip, true, 0);
-        uint32_t s1, st1;
-        if (tile_decode(P, groups, nitems, 1, s1, st1)) request(1, s1, st1, s1 != cur_set, 1);
-    }
-
-    uint32_t tb = 0;                                      // table buffer of the current tile (flips at every set change)
-    for (uint32_t t = 0;; ++t) {
-        const uint32_t buf = t & 1u;
-        uint4* tile = smem + buf * kTileChunks;
-        mbar_wait(bar + buf, (t >> 1) & 1u);
-        const bool active = warp_col_active(P, wp, cur_strip);
-        const uint4* tw0 = tabs + (tb * NXF) * R;
-        const uint4* tw1 = tw0 + R;
-        RoundRegs r;
-        if (active) warp_phase(P, 0, tid, cur_set, wa, tile, tw0, tw1, r, zero);
-        __syncwarp();
-        if (active && !P.debug_skip_math) warp_phase(P, 1, tid, cur_set, wa, tile, tw0, tw1, r, zero);
-        if (LR > kStages && !P.debug_skip_math) {
-            if (active) warp_phase(P, 2, tid, cur_set, wa, tile, tw0, tw1, r, zero);
-            __syncwarp();
-            if (active) warp_phase(P, 3, tid, cur_set, wa, tile, tw0, tw1, r, zero);
-            __syncwarp();
-            if (active) warp_phase(P, 4, tid, cur_set, wa, tile, tw0, tw1, r, zero);
-            if (NXF == 2) {
-                if (active) warp_phase(P, 5, tid, cur_set, wa, tile, tw0, tw1, r, zero);
-                __syncwarp();
-                if (active) warp_phase(P, 6, tid, cur_set, wa, tile, tw0, tw1, r, zero);
-                __syncwarp();
-                if (active) warp_phase(P, 7, tid, cur_set, wa, tile, tw0, tw1, r, zero);
-            }
-        }
-        if (active) warp_phase(P, 8, tid, cur_set, wa, tile, tw0, tw1, r, zero);
-        fence_proxy_async();                              // our generic-proxy writes, before the async-proxy (TMA) read
-        __syncwarp();
-
-        uint32_t n1_set = 0, n1_strip = 0;
-        const bool has_n1 = tile_decode(P, groups, nitems, t + 1, n1_set, n1_strip);
-        uint32_t is_last = 0;
-        if (lane == 0) { __threadfence_block(); is_last = (atomicAdd(done + buf, 1u) == (uint32_t)(kThreads / 32 - 1)) ? 1u : 0u; }
-        is_last = __shfl_sync(0xffffffffu, is_last, 0);
-        if (is_last) {                                    // every warp has written its columns: this warp does the tile's I/O
-            if (lane == 0) {
-                __threadfence_block();
-                atomicExch(done + buf, 0u);
-                fence_proxy_async();
-#pragma unroll
-                for (uint32_t cb = 0; cb < kColBlocks; ++cb)
-#pragma unroll
-                    for (uint32_t rb = 0; rb < kRowBoxes; ++rb)
-                        tma_store_3d(box_ptr(buf, cb, rb), &dst_map, cur_strip * kWt + cb * kWb, rb * kRowsBox, cur_set);
-                bulk_commit();
-                uint32_t n2_set = 0, n2_strip = 0;
-                if (has_n1 && tile_decode(P, groups, nitems, t + 2, n2_set, n2_strip)) {
-                    bulk_wait_read_all();                 // the store has read this buffer: refill it with the tile after next
-                    const uint32_t tb1 = tb ^ (n1_set != cur_set ? 1u : 0u);
-                    request(buf, n2_set, n2_strip, n2_set != n1_set, tb1 ^ 1u);
-                } else {
-                    bulk_wait_all();
-                }
-            }
-            __syncwarp();
-        }
-        if (!has_n1) break;
-        if (n1_set != cur_set) tb ^= 1u;
-        cur_set = n1_set; cur_strip = n1_strip;
-    }
-}
-
 // One thread per table entry: tables[set][xfi][idx] = g^exponent (entry 0 of every table is unused).
 __global__ void build_tables_kernel(const PassParams P, uint4* out, uint32_t nsets_tab)
 {
@@ -447,7 +299,7 @@ __global__ void build_tables_kernel(const PassParams P, uint4* out, uint32_t nse
         const uint32_t idx = (uint32_t)(i & (R - 1));
         const uint32_t xfi = (uint32_t)((i >> P.log_r) % P.nxf);
         const uint32_t set = (uint32_t)((i >> P.log_r) / P.nxf);
-        out[i] = idx ? P.tw[table_entry_exponent(P, xfi, set, idx)] : make_uint4(0, 0, 0, 0);
+        out[i] = idx ? stage_entry(P.tw[table_entry_exponent(P, xfi, set, idx)]) : make_uint4(0, 0, 0, 0);
     }
 }
 
@@ -483,59 +335,21 @@ static EncodeTiledFn encode_tiled()
     return fn;
 }
 
-// 3-D view of a buffer: [word][row within set][set].  warp_layout: column blocks of <= 32 words with the hardware swizzle
-// that ntt_warp.cuh's cell8() assumes (64-byte rows: SWIZZLE_64B, 128-byte rows: SWIZZLE_128B).
-static bool make_tensor_map(const PassParams& P, bool dst, bool warp_layout, CUtensorMap* map)
+// 3-D view of the source buffer: [word][row within set][set]; box = one tile row strip of <= 256 rows.
+static bool make_tensor_map(const PassParams& P, CUtensorMap* map)
 {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return false;
     const uint32_t R = 1u << P.log_r, Wt = 16384u >> P.log_r;
-    const uint32_t Wb = warp_layout ? (Wt < 32u ? Wt : 32u) : Wt;
-    if (Wb > 256) return false;
-    const cuuint64_t row_bytes = (cuuint64_t)P.pitch4 * 16;
-    const uint32_t rstride = dst ? P.dst_row_stride : P.src_row_stride, sstride = dst ? P.dst_set_stride : P.src_set_stride;
-    cuuint64_t gdim[3] = {(cuuint64_t)P.s4 * 4, R, P.nsets};
-    cuuint64_t gstr[2] = {(cuuint64_t)rstride * row_bytes, P.nsets > 1 ? (cuuint64_t)sstride * row_bytes : (cuuint64_t)rstride * row_bytes * R};
-    cuuint32_t box[3] = {Wb, R < 256u ? R : 256u, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    if (gstr[0] >= (1ull << 40) || gstr[1] >= (1ull << 40)) return false;
-    const CUtensorMapSwizzle sw = !warp_layout ? CU_TENSOR_MAP_SWIZZLE_NONE : (Wb * 4 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
-    void* base = dst ? (void*)P.dst : (void*)P.src;
-    CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      sw, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return rc == CUDA_SUCCESS;
-}
-
-// [word][row within set][set] view of the source with a box one work item wide (strips_per_item strips), for L2 prefetch
-static bool make_prefetch_map(const PassParams& P, CUtensorMap* map)
-{
-    EncodeTiledFn enc = encode_tiled();
-    if (!enc) return false;
-    const uint32_t R = 1u << P.log_r, Wt = 16384u >> P.log_r;
-    const uint32_t W = Wt * P.strips_per_item;
-    if (W > 256) return false;
+    if (Wt > 256) return false;
     const cuuint64_t row_bytes = (cuuint64_t)P.pitch4 * 16;
     cuuint64_t gdim[3] = {(cuuint64_t)P.s4 * 4, R, P.nsets};
     cuuint64_t gstr[2] = {(cuuint64_t)P.src_row_stride * row_bytes, P.nsets > 1 ? (cuuint64_t)P.src_set_stride * row_bytes : (cuuint64_t)P.src_row_stride * row_bytes * R};
-    cuuint32_t box[3] = {W, R < 256u ? R : 256u, 1};
+    cuuint32_t box[3] = {Wt, R < 256u ? R : 256u, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     if (gstr[0] >= (1ull << 40) || gstr[1] >= (1ull << 40)) return false;
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void*)P.src, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-template <int LR, int NXF>
-static cudaError_t launch_warp_inst(const PassParams& P, const CUtensorMap& smap, const CUtensorMap& dmap, const CUtensorMap& pmap, unsigned grid, cudaStream_t stream)
-{
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(ntt_pass_warp_kernel<LR, NXF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             2 * kTileBytes + 2 * NXF * (16 << LR) + 32);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    ntt_pass_warp_kernel<LR, NXF><<<grid, kThreads, 2 * kTileBytes + 2 * NXF * (16 << LR) + 32, stream>>>(P, smap, dmap, pmap);
-    return cudaGetLastError();
 }
 
 static size_t dual_smem_bytes(const PassParams& P)
@@ -556,7 +370,7 @@ static cudaError_t launch_dual_inst(const PassParams& P, const CUtensorMap& map,
 }
 
 template <int LR, int NXF, int TMA>
-static cudaError_t launch_inst(const PassParams& P, const CUtensorMap& map, const CUtensorMap& pmap, unsigned grid, cudaStream_t stream)
+static cudaError_t launch_inst(const PassParams& P, const CUtensorMap& map, unsigned grid, cudaStream_t stream)
 {
     static bool attr_set = false;
     if (!attr_set) {
@@ -566,11 +380,20 @@ static cudaError_t launch_inst(const PassParams& P, const CUtensorMap& map, cons
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    ntt_pass_kernel<LR, NXF, TMA><<<grid, kThreads, pass_smem_bytes(P), stream>>>(P, map, pmap);
+    ntt_pass_kernel<LR, NXF, TMA><<<grid, kThreads, pass_smem_bytes(P), stream>>>(P, map);
     return cudaGetLastError();
 }
 
-cudaError_t launch_pass(const PassParams& Pin, int num_sms, cudaStream_t stream)
+// name of the instantiation a pass is dispatched to, for the per-kernel lines of the benchmark (static storage)
+static const char* kernel_name(bool dual, uint32_t lr, uint32_t a, uint32_t b)
+{
+    static char names[2][6][3][3][48];
+    char* n = names[dual ? 1 : 0][lr - 5][a][b];
+    if (!n[0]) { if (dual) snprintf(n, 48, "ntt_pass_dual_kernel<%u,%u>", lr, a); else snprintf(n, 48, "ntt_pass_kernel<%u,%u,%u>", lr, a, b); }
+    return n;
+}
+
+cudaError_t launch_pass(const PassParams& Pin, int num_sms, cudaStream_t stream, const char** kernel)
 {
     PassParams P = Pin;
     const uint32_t groups = (P.nstrips + P.strips_per_item - 1) / P.strips_per_item;
@@ -581,33 +404,16 @@ cudaError_t launch_pass(const PassParams& Pin, int num_sms, cudaStream_t stream)
     if (grid == 0) return cudaSuccess;
     const unsigned g = (unsigned)grid;
     if (!P.tables) return cudaErrorInvalidValue;
-    CUtensorMap map, pmap;
-    memset(&map, 0, sizeof map); memset(&pmap, 0, sizeof pmap);
-    static const int pf_env = getenv("FASTECC_B200_L2_PREFETCH") ? atoi(getenv("FASTECC_B200_L2_PREFETCH")) : -1;
-    // default: prefetch for passes whose rows are far apart (strided row sets); contiguous row sets stream well already
-    P.l2_prefetch = (pf_env > 0) && P.strips_per_item > 1 && make_prefetch_map(P, &pmap) ? 1u : 0u;      // off by default: measured no gain, 2x DRAM reads
-    static const bool skip_math = getenv("FASTECC_B200_DEBUG_SKIP_MATH") != nullptr;                         // memory-pattern ceiling experiment (wrong results!)
-    P.debug_skip_math = skip_math ? 1u : 0u;
+    CUtensorMap map;
+    memset(&map, 0, sizeof map);
     static const bool no_tma = getenv("FASTECC_B200_NO_TMA") != nullptr;
-    static const bool v8 = !(getenv("FASTECC_B200_KERNEL") && !strcmp(getenv("FASTECC_B200_KERNEL"), "warp"));   // default: CTA-level schedule; "warp": ntt_warp.cuh
-    if (!v8 && !no_tma && !P.log_g) {                    // (the warp kernel writes tiles back with TMA stores: no per-row destination GPU)
-        CUtensorMap smap, dmap;
-        if (make_tensor_map(P, false, true, &smap) && make_tensor_map(P, true, true, &dmap)) {
-            const unsigned gw = (unsigned)((unsigned long long)num_sms < nitems ? (unsigned long long)num_sms : nitems);      // one CTA per SM
-#define FECC_WCASE(L) case L: return P.nxf == 2 ? launch_warp_inst<L, 2>(P, smap, dmap, pmap, gw, stream) : launch_warp_inst<L, 1>(P, smap, dmap, pmap, gw, stream);
-            switch (P.log_r) {
-                FECC_WCASE(5) FECC_WCASE(6) FECC_WCASE(7) FECC_WCASE(8) FECC_WCASE(9) FECC_WCASE(10)
-                default: return cudaErrorInvalidValue;
-            }
-#undef FECC_WCASE
-        }
-    }
-    const bool tma = !no_tma && P.log_r >= 6 && make_tensor_map(P, false, false, &map);
+    const bool tma = !no_tma && P.log_r >= 6 && make_tensor_map(P, &map);
     if (P.log_g && !tma) return cudaErrorNotSupported;          // sharded stores exist only in the TMA instantiations
     // single-transform passes with enough tiles to keep both groups of every SM busy: the dual schedule (3 tile buffers / SM)
     static const bool no_dual = getenv("FASTECC_B200_KERNEL") && !strcmp(getenv("FASTECC_B200_KERNEL"), "cta");
     if (tma && !no_dual && P.nxf == 1 && dual_smem_bytes(P) <= 232448 && nitems * P.strips_per_item >= 4ull * num_sms) {
         const unsigned gd = (unsigned)((unsigned long long)num_sms < nitems ? (unsigned long long)num_sms : nitems);
+        if (kernel) *kernel = kernel_name(true, P.log_r, P.log_g ? 1 : 0, 0);
         switch (P.log_r) {
             case 6: return P.log_g ? launch_dual_inst<6, 1>(P, map, gd, stream) : launch_dual_inst<6, 0>(P, map, gd, stream);
             case 7: return P.log_g ? launch_dual_inst<7, 1>(P, map, gd, stream) : launch_dual_inst<7, 0>(P, map, gd, stream);
@@ -617,10 +423,11 @@ cudaError_t launch_pass(const PassParams& Pin, int num_sms, cudaStream_t stream)
             default: break;
         }
     }
+    if (kernel) *kernel = kernel_name(false, P.log_r, P.nxf, tma ? (P.log_g ? 2 : 1) : 0);
 #define FECC_CASE(L) case L: \
-        if (tma && P.log_g) return P.nxf == 2 ? launch_inst<L, 2, 2>(P, map, pmap, g, stream) : launch_inst<L, 1, 2>(P, map, pmap, g, stream); \
-        if (tma) return P.nxf == 2 ? launch_inst<L, 2, 1>(P, map, pmap, g, stream) : launch_inst<L, 1, 1>(P, map, pmap, g, stream); \
-        else     return P.nxf == 2 ? launch_inst<L, 2, 0>(P, map, pmap, g, stream) : launch_inst<L, 1, 0>(P, map, pmap, g, stream);
+        if (tma && P.log_g) return P.nxf == 2 ? launch_inst<L, 2, 2>(P, map, g, stream) : launch_inst<L, 1, 2>(P, map, g, stream); \
+        if (tma) return P.nxf == 2 ? launch_inst<L, 2, 1>(P, map, g, stream) : launch_inst<L, 1, 1>(P, map, g, stream); \
+        else     return P.nxf == 2 ? launch_inst<L, 2, 0>(P, map, g, stream) : launch_inst<L, 1, 0>(P, map, g, stream);
     switch (P.log_r) {
         FECC_CASE(5) FECC_CASE(6) FECC_CASE(7) FECC_CASE(8) FECC_CASE(9) FECC_CASE(10)
         default: return cudaErrorInvalidValue;

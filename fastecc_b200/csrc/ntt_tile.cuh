@@ -62,7 +62,7 @@ struct Xform { uint32_t z, t0, t1; };        // tile root g^z; input twist g^(t0
 struct PassParams {
     const uint32_t* src;
     uint32_t*       dst;
-    const uint4*    tw;                      // g^e for e in [0, 2^20): {w, Whi, Wlo, 0}
+    const uint4*    tw;                      // g^e for e in [0, 2^20): {w, Whi, Wlo, 0}  (gf::Tw)
     uint32_t pitch4;                         // row pitch in 16-byte chunks
     uint32_t s4;                             // valid 16-byte chunks per row (ceil(SIZE/4))
     uint32_t log_r;                          // log2(rows per tile), 5..10
@@ -73,12 +73,10 @@ struct PassParams {
     uint32_t nxf;                            // 1, or 2 = two transforms back to back on the same tile
     Xform    xf[2];
     uint32_t prescale;                       // multiply every input word by the constant below (1/N)
-    uint32_t pw, pwhi, pwlo;
+    uint32_t pw, pwp_lo, pwp_hi;             // the constant and its quotient factor wp (gf::mul_h); set_prescale() in plan.h
     uint32_t canonical_out;                  // reduce stored words to [0,P)
-    const uint4* tables;                     // per-set stage tables [set][xfi][R], built once per plan (build_tables_kernel)
+    const uint4* tables;                     // per-set stage tables [set][xfi][R] of stage_entry()s, built once per plan (build_tables_kernel)
     uint32_t table_set_stride;               // uint4 entries between consecutive sets' tables (0: every set shares set 0's)
-    uint32_t debug_skip_math;                // experiments only: move the tiles without transforming them
-    uint32_t l2_prefetch;                    // 1: request an L2 prefetch of the next work item's column block (set by launch_pass)
     uint32_t use_tma;                        // 1: tile/table loads by TMA (cp.async.bulk[.tensor]) + mbarrier; 0: 16-byte cp.async
     // One transform sharded over 2^log_g GPUs with the exchange fused into the stores (plan_encode_shard_p2p): output
     // element e of a set goes to buffer peers[e mod G] (peer-mapped device memory, NVLink), row
@@ -143,15 +141,28 @@ FECC_HD uint32_t table_exponent(uint32_t idx, uint32_t LR, uint32_t z, uint32_t 
 
 FECC_HD uint2 canon2(uint2 v) { v.x = gf::canon(v.x); v.y = gf::canon(v.y); return v; }
 
+// A stage-table entry, as the pass kernels read it from shared memory: {w, 0, lo32(wp), hi32(wp)} with wp the double
+// of gf::mul_h.  Made from an entry {w, Whi, Wlo, 0} of the global power table (build_tables_kernel, CPU emulation).
+FECC_HD uint4 stage_entry(const uint4& t)
+{
+#if defined(FECC_MUL_BARRETT)            // A/B experiment: the round-1 integer-only product (gf::mul)
+    return t;
+#endif
+    uint4 e; e.x = t.x; e.y = 0;
+    gf::wp_bits(t.y, t.z, e.z, e.w);
+    return e;
+}
+
 // One butterfly on a word pair:  (a, b) <- (a + w*b, a - w*b)
-FECC_HD void bfly2(uint2& a, uint2& b, const uint4& w, uint32_t zero)
+FECC_HD void bfly2(uint2& a, uint2& b, const uint4& w)
 {
     uint32_t v;
-    v = gf::mul(b.x, w.x, w.y, w.z, zero); b.x = gf::subl(a.x, v); a.x = gf::addl(a.x, v);
-#if defined(FECC_MIXED_MONT)
-    v = gf::mul_mont(b.y, w.w);            b.y = gf::subl(a.y, v); a.y = gf::addl(a.y, v);
+#if defined(FECC_MUL_BARRETT)
+    v = gf::mul(b.x, w.x, w.y, w.z); b.x = gf::subl(a.x, v); a.x = gf::addl(a.x, v);
+    v = gf::mul(b.y, w.x, w.y, w.z); b.y = gf::subl(a.y, v); a.y = gf::addl(a.y, v);
 #else
-    v = gf::mul(b.y, w.x, w.y, w.z, zero); b.y = gf::subl(a.y, v); a.y = gf::addl(a.y, v);
+    v = gf::mul_h(b.x, w.x, w.z, w.w); b.x = gf::subl(a.x, v); a.x = gf::addl(a.x, v);
+    v = gf::mul_h(b.y, w.x, w.z, w.w); b.y = gf::subl(a.y, v); a.y = gf::addl(a.y, v);
 #endif
 }
 // the same with twiddle 1: b only has to be brought into [0,P) (two ALU instructions) for the lazy add/sub
@@ -190,7 +201,7 @@ struct RoundRegs { uint2 x[kRows]; };
 // current transform (shared memory on the device).  BREV: the registers are numbered in the order of the PREVIOUS
 // transform's last round (fused tiles): this transform's slot i is register brev5(i).
 template <bool BREV>
-FECC_HD void round_compute(uint2 (&x)[kRows], const RoundCtx& c, const uint4* tw, uint32_t zero)
+FECC_HD void round_compute(uint2 (&x)[kRows], const RoundCtx& c, const uint4* tw)
 {
     const uint32_t sb = 1u << c.lb;                     // table stride between consecutive in-thread twiddles
     const uint4* tb = tw + c.jlow;
@@ -206,7 +217,7 @@ FECC_HD void round_compute(uint2 (&x)[kRows], const RoundCtx& c, const uint4* tw
                 for (int hi = 0; hi < (16 >> beta); ++hi) {
                     const int i0 = (hi << (beta + 1)) | m;
                     const int i1 = i0 | (1 << beta);
-                    bfly2(x[BREV ? brev5(i0) : i0], x[BREV ? brev5(i1) : i1], w, zero);
+                    bfly2(x[BREV ? brev5(i0) : i0], x[BREV ? brev5(i1) : i1], w);
                 }
             }
         }
@@ -217,14 +228,14 @@ FECC_HD void round_compute(uint2 (&x)[kRows], const RoundCtx& c, const uint4* tw
 // known at compile time because lb = 0 makes the table index depend on the in-thread index only (31 of the 80
 // butterflies of a full round).  The uniform pre-scale by 1/N (RS.cpp:51,54) is folded into stage 0, whose 16
 // butterflies then cost two products each instead of one product plus two pre-scale products.
-FECC_HD void round0_plain(uint2 (&x)[kRows], const RoundCtx& c, const uint4* tw, bool prescale, uint32_t pw, uint32_t pwhi, uint32_t pwlo, uint32_t zero)
+FECC_HD void round0_plain(uint2 (&x)[kRows], const RoundCtx& c, const uint4* tw, bool prescale, uint32_t pw, uint32_t pwp_lo, uint32_t pwp_hi)
 {
 #pragma unroll
     for (int hi = 0; hi < 16; ++hi) {                       // stage 0: all twiddles are 1
         uint2& a = x[2 * hi]; uint2& b = x[2 * hi + 1];
         if (prescale) {
-            a.x = gf::mul(a.x, pw, pwhi, pwlo, zero); a.y = gf::mul(a.y, pw, pwhi, pwlo, zero);
-            b.x = gf::mul(b.x, pw, pwhi, pwlo, zero); b.y = gf::mul(b.y, pw, pwhi, pwlo, zero);
+            a.x = gf::mul_h(a.x, pw, pwp_lo, pwp_hi); a.y = gf::mul_h(a.y, pw, pwp_lo, pwp_hi);
+            b.x = gf::mul_h(b.x, pw, pwp_lo, pwp_hi); b.y = gf::mul_h(b.y, pw, pwp_lo, pwp_hi);
             uint32_t t;
             t = b.x; b.x = gf::subl(a.x, t); a.x = gf::addl(a.x, t);
             t = b.y; b.y = gf::subl(a.y, t); a.y = gf::addl(a.y, t);
@@ -244,17 +255,17 @@ FECC_HD void round0_plain(uint2 (&x)[kRows], const RoundCtx& c, const uint4* tw,
                 for (int hi = 0; hi < (16 >> beta); ++hi) {
                     const int i0 = (hi << (beta + 1)) | m;
                     const int i1 = i0 | (1 << beta);
-                    if (m) bfly2(x[i0], x[i1], w, zero); else bfly2_trivial(x[i0], x[i1]);
+                    if (m) bfly2(x[i0], x[i1], w); else bfly2_trivial(x[i0], x[i1]);
                 }
             }
         }
     }
 }
 
-FECC_HD void prescale_all(uint2 (&x)[kRows], uint32_t w, uint32_t whi, uint32_t wlo, uint32_t zero)
+FECC_HD void prescale_all(uint2 (&x)[kRows], uint32_t w, uint32_t wp_lo, uint32_t wp_hi)
 {
 #pragma unroll
-    for (int i = 0; i < kRows; ++i) { x[i].x = gf::mul(x[i].x, w, whi, wlo, zero); x[i].y = gf::mul(x[i].y, w, whi, wlo, zero); }
+    for (int i = 0; i < kRows; ++i) { x[i].x = gf::mul_h(x[i].x, w, wp_lo, wp_hi); x[i].y = gf::mul_h(x[i].y, w, wp_lo, wp_hi); }
 }
 
 // P.xf[xfi] with a runtime xfi would make the compiler copy the kernel parameters to local memory
@@ -355,7 +366,7 @@ FECC_HD void round_read(const PassParams& P, uint32_t k, uint32_t brev, uint32_t
 }
 
 // (b) the butterflies of a step
-FECC_HD void round_math(const PassParams& P, const Step st, uint32_t tid, uint32_t set, const uint4* tw0, const uint4* tw1, RoundRegs& r, uint32_t zero)
+FECC_HD void round_math(const PassParams& P, const Step st, uint32_t tid, uint32_t set, const uint4* tw0, const uint4* tw1, RoundRegs& r)
 {
     const uint32_t LR = P.log_r;
     const ThreadPos tp = thread_pos(LR, tid);
@@ -365,14 +376,14 @@ FECC_HD void round_math(const PassParams& P, const Step st, uint32_t tid, uint32
     const bool plain = ((xf.t0 + set * xf.t1) & (gf::M - 1)) == 0;
     const uint4* tw = st.xfi ? tw1 : tw0;
     if (st.k == 0 && plain) {
-        round0_plain(r.x, c, tw, first && P.prescale, P.pw, P.pwhi, P.pwlo, zero);
+        round0_plain(r.x, c, tw, first && P.prescale, P.pw, P.pwp_lo, P.pwp_hi);
     } else {
-        if (first && P.prescale) prescale_all(r.x, P.pw, P.pwhi, P.pwlo, zero);
-        round_compute<false>(r.x, c, tw, zero);
+        if (first && P.prescale) prescale_all(r.x, P.pw, P.pwp_lo, P.pwp_hi);
+        round_compute<false>(r.x, c, tw);
     }
     if (st.fused) {                                     // round 0 of the second transform on the same registers
         const RoundCtx c1 = make_round(LR, 0, 0);       // lb = 0: no dependence on the thread's position
-        round_compute<true>(r.x, c1, tw1, zero);
+        round_compute<true>(r.x, c1, tw1);
     }
 }
 

@@ -64,6 +64,12 @@ inline PassParams base_pass(const Buffers& b, uint32_t log_r)
 }
 
 constexpr uint32_t kM = gf::M;
+inline void set_prescale(PassParams& p, uint32_t c)                     // multiply every input word of the pass by c
+{
+    const gf::Tw t = gf::make_tw(c);
+    p.prescale = 1; p.pw = t.w;
+    gf::wp_bits(t.whi, t.wlo, p.pwp_lo, p.pwp_hi);
+}
 inline uint32_t emod(long long e) { return (uint32_t)(((e % (long long)kM) + kM) % kM); }
 
 // Standalone transform.  Result lands in b.x; b.y is scratch (needed only when N > 1024).
@@ -105,7 +111,7 @@ inline std::vector<PassParams> plan_encode(const Buffers& b, size_t N)
     std::vector<PassParams> v;
     const uint32_t LN = ilog2(N);
     const long long q = (long long)(kM / (2 * N));                      // rho = root_2N = g^q, w = g^(2q)
-    const gf::Tw invN = gf::make_tw(gf::inv((uint32_t)N));              // GF_Inv(N), RS.cpp:51
+    const uint32_t invN = gf::inv((uint32_t)N);                         // GF_Inv(N), RS.cpp:51
     if (LN <= kMaxLogR) {
         PassParams a = base_pass(b, LN);
         a.src = b.x; a.dst = b.x; a.nsets = 1;
@@ -113,7 +119,7 @@ inline std::vector<PassParams> plan_encode(const Buffers& b, size_t N)
         a.nxf = 2;
         a.xf[0] = Xform{emod(-2 * q), 0, 0};
         a.xf[1] = Xform{emod(2 * q), emod(q), 0};
-        a.prescale = 1; a.pw = invN.w; a.pwhi = invN.whi; a.pwlo = invN.wlo;
+        set_prescale(a, invN);
         a.canonical_out = 1;
         v.push_back(a);
         return v;
@@ -124,7 +130,7 @@ inline std::vector<PassParams> plan_encode(const Buffers& b, size_t N)
     a.src = b.x; a.dst = b.x; a.nsets = (uint32_t)N2;
     a.src_set_stride = a.dst_set_stride = 1; a.src_row_stride = a.dst_row_stride = N2;
     a.xf[0] = Xform{emod(-2 * q * (long long)N2), 0, 0};
-    a.prescale = 1; a.pw = invN.w; a.pwhi = invN.whi; a.pwlo = invN.wlo;
+    set_prescale(a, invN);
     v.push_back(a);
     PassParams bc = base_pass(b, L2);
     bc.src = b.x; bc.dst = b.x; bc.nsets = (uint32_t)N1;
@@ -194,14 +200,13 @@ inline PassParams plan_encode_shard(const Buffers& b, size_t N, uint32_t G, uint
     const long long q = (long long)(kM / (2 * N));
     const uint32_t L1 = split_l1(LN), L2 = LN - L1;
     const uint32_t N1 = 1u << L1, N2 = 1u << L2;
-    const gf::Tw invN = gf::make_tw(gf::inv((uint32_t)N));
     PassParams p;
     if (which == 0) {
         p = base_pass(b, L1);
         p.nsets = N2 / G;
         p.src_set_stride = p.dst_set_stride = 1; p.src_row_stride = p.dst_row_stride = N2 / G;
         p.xf[0] = Xform{emod(-2 * q * (long long)N2), 0, 0};
-        p.prescale = 1; p.pw = invN.w; p.pwhi = invN.whi; p.pwlo = invN.wlo;
+        set_prescale(p, gf::inv((uint32_t)N));
     } else if (which == 1) {
         p = base_pass(b, L2);
         p.nsets = N1 / G;

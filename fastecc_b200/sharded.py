@@ -18,16 +18,22 @@ from __future__ import annotations
 from typing import Callable
 
 
-def geometry(N: int, G: int):
+def _geometry(N: int, G: int):
+    """(N1, N2, fused_exchange_ok) from the planner itself (csrc/plan.h split_l1 / shard_supported through the C ABI), so
+    that the exchanges below can never disagree with the passes' decomposition (e.g. under FASTECC_B200_SPLIT)."""
+    import ctypes
+    import fastecc_b200 as fe
     LN = N.bit_length() - 1
     if N != 1 << LN or LN < 11 or LN > 19 or G < 2 or G & (G - 1):
         raise ValueError("sharded encode needs N = 2^11..2^19 and a power-of-two number of ranks")
-    L1 = min(9, (LN + 1) // 2)                       # csrc/plan.h split_l1()
-    L1 = max(L1, LN - 10, 5)
-    N1, N2 = 1 << L1, 1 << (LN - L1)
-    if N2 % G:
-        raise ValueError("N2 must be a multiple of the number of ranks")
-    return N1, N2
+    n1, n2, ok = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_int()
+    if fe.lib().fastecc_b200_shard_geometry(N, G, ctypes.byref(n1), ctypes.byref(n2), ctypes.byref(ok)) != 0:
+        raise ValueError("N2 = %d must be a multiple of the number of ranks" % n2.value)
+    return n1.value, n2.value, bool(ok.value)
+
+
+def geometry(N: int, G: int):
+    return _geometry(N, G)[:2]
 
 
 def _all_to_all(send, group):
@@ -86,11 +92,9 @@ def gpu_pass_runner(N: int, G: int, rank: int):
 def p2p_supported(N: int, G: int) -> bool:
     """csrc/plan.h shard_p2p_supported(): <= 8 ranks and every thread's 32 output rows on one rank for both tile heights."""
     try:
-        N1, N2 = geometry(N, G)
+        return _geometry(N, G)[2]
     except ValueError:
         return False
-    lg = G.bit_length() - 1
-    return G <= 8 and N1.bit_length() - 1 >= 5 + lg and N2.bit_length() - 1 >= 5 + lg
 
 
 class _RawCudaBuffer:

@@ -7,6 +7,11 @@
  * returns a human-readable message for the calling thread.  There is NO CPU fallback: without a usable CUDA
  * device every compute entry point fails with FASTECC_B200_ECUDA.
  *
+ * Concurrency: the context is process-wide.  The host (T**) entry points are serialised by an internal lock (they share one
+ * staging buffer and three internal streams).  The *_dev entry points are asynchronous on the caller's stream and may be
+ * called from several threads / on several streams: the shared scratch buffers and the lazily built twiddle tables are
+ * ordered across streams with events (two transforms that need the same scratch buffer run one after the other).
+ *
  * Data model (same as the reference): N blocks of SIZE 32-bit words, words are elements of
  * GF(P), P = 0xFFF00001, the transform runs across blocks independently for every word column.  Inputs may be
  * any 32-bit values (they are taken mod P); outputs are canonical residues in [0, P).
@@ -61,6 +66,12 @@ int fastecc_b200_rs_encode(uint32_t** data, size_t N, size_t SIZE_words);
 int fastecc_b200_ntt_u32_dev  (uint32_t* d_blocks, size_t N, size_t SIZE_words, size_t pitch_words, int inverse, void* stream);
 int fastecc_b200_rs_encode_dev(uint32_t* d_blocks, size_t N, size_t SIZE_words, size_t pitch_words, void* stream);
 
+/* Measurement variant of fastecc_b200_rs_encode_dev (bench.py's per-kernel roofline): the same encode with a CUDA event
+ * between the passes; synchronises the stream.  In: *n_passes = capacity of pass_ms / pass_kernel (may be NULL).  Out: the
+ * duration of every pass kernel in ms, the name of the instantiation it ran as (static strings) and their number. */
+int fastecc_b200_rs_encode_dev_timed(uint32_t* d_blocks, size_t N, size_t SIZE_words, size_t pitch_words, void* stream,
+                                     float* pass_ms, const char** pass_kernel, int* n_passes);
+
 /* ---- fewer parity blocks than data blocks ------------------------------------------------------
  * The reference only describes this (RS.cpp:65-66, NTT.md:46-49: "in order to compute only even-indexed points ...").
  * N data blocks in, M = N / 2^k parity blocks out: parity block j' is parity block (N/M)*j' of the full N -> N encode,
@@ -108,11 +119,23 @@ int fastecc_b200_rs_encode_shard_pass(uint32_t* d_local, size_t N, int n_ranks, 
  * both factors of N = N1*N2 (csrc/plan.h split_l1) at least 32*n_ranks, so that the 32 rows a thread stores go to one rank. */
 int fastecc_b200_rs_encode_shard_pass_p2p(const uint32_t* d_src, uint32_t* const* d_peers, size_t N, int n_ranks, int rank,
                                           size_t SIZE_words, size_t pitch_words, int which, void* stream);
+/* The decomposition N = N1 * N2 the passes use (csrc/plan.h split_l1, FASTECC_B200_SPLIT honoured), for callers that do the
+ * exchange themselves; *fused_exchange_ok = 1 when the _p2p passes support (N, n_ranks).  Fails if N cannot be sharded. */
+int fastecc_b200_shard_geometry(size_t N, int n_ranks, size_t* N1, size_t* N2, int* fused_exchange_ok);
+/* cudaMemcpy2DAsync between pinned host memory and a device buffer (column chunks of a block array), for pipelined
+ * host <-> device staging around the sharded passes (fastecc_b200/sharded.py encode_host). */
+int fastecc_b200_copy2d_async(void* dst, size_t dst_pitch_bytes, const void* src, size_t src_pitch_bytes, size_t width_bytes, size_t rows,
+                              int to_device, void* stream);
 void* fastecc_b200_dev_alloc(size_t bytes);                       /* cudaMalloc: exportable, unlike a caching-allocator block */
 void  fastecc_b200_dev_free(void* d_ptr);
 int   fastecc_b200_ipc_export(void* d_ptr, void* handle64);       /* 64-byte cudaIpcMemHandle_t */
 int   fastecc_b200_ipc_open(const void* handle64, void** d_ptr);  /* in another process on the same node */
 int   fastecc_b200_ipc_close(void* d_ptr);
+
+/* Replaces  uint32_t hash(T** data, size_t N, size_t SIZE)   main.cpp:203-212: the rolling checksum the reference's
+ * driver prints before and after a transform, walked through data[i] in block order (host memory).  Sequential by
+ * construction (about one second for 2 GiB); used to compare results with the reference's published / golden hashes. */
+uint32_t fastecc_b200_hash_u32(uint32_t* const* data, size_t N, size_t SIZE_words);
 
 /* Counters for benchmarking: kernels launched by this library since init (all entry points). */
 unsigned long long fastecc_b200_kernel_launches(void);

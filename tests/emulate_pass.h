@@ -4,7 +4,6 @@
 #include <vector>
 #include <algorithm>
 #include "plan.h"
-#include "ntt_warp.cuh"
 using namespace fecc;
 
 static void emulate_pass(PassParams P)
@@ -14,7 +13,7 @@ static void emulate_pass(PassParams P)
     const uint32_t nst = table_sets(P);
     std::vector<uint4> tables((size_t)nst * P.nxf * R);
     for (uint32_t set = 0; set < nst; ++set) for (uint32_t x = 0; x < P.nxf; ++x) for (uint32_t idx = 0; idx < R; ++idx)
-        tables[((size_t)set * P.nxf + x) * R + idx] = idx ? P.tw[table_entry_exponent(P, x, set, idx)] : make_uint4(0, 0, 0, 0);
+        tables[((size_t)set * P.nxf + x) * R + idx] = idx ? stage_entry(P.tw[table_entry_exponent(P, x, set, idx)]) : make_uint4(0, 0, 0, 0);
     P.tables = tables.data();
     P.table_set_stride = nst > 1 ? (P.nxf << P.log_r) : 0u;
 
@@ -39,7 +38,7 @@ static void emulate_pass(PassParams P)
                     if (thread_active(P, tid, strip)) round_read(P, st.k, st.xfi == 0, tid, tile.data(), regs[tid]);
                 for (uint32_t tid = 0; tid < kThreads; ++tid) {
                     if (!thread_active(P, tid, strip)) continue;
-                    round_math(P, st, tid, set, tabs.data(), tabs.data() + R, regs[tid], 0);
+                    round_math(P, st, tid, set, tabs.data(), tabs.data() + R, regs[tid]);
                     if (last) round_write_global(P, st, tid, set, strip, regs[tid]);
                     else      round_write_tile(P, st.k, st.xfi == 0, tid, tile.data(), regs[tid]);
                 }
@@ -48,46 +47,3 @@ static void emulate_pass(PassParams P)
     }
 }
 
-
-// Warp-private schedule (ntt_warp.cuh / ntt_pass_warp_kernel): TMA load into the swizzled tile, the nine phases of
-// warp_phase() (each run for all 256 threads before the next: a superset of the kernel's __syncwarp ordering), TMA store.
-static void emulate_pass_warp(PassParams P)
-{
-    const uint32_t LR = P.log_r, R = 1u << LR, Wt = 16384u >> LR;
-    const uint32_t nst = table_sets(P);
-    std::vector<uint4> tables((size_t)nst * P.nxf * R);
-    for (uint32_t set = 0; set < nst; ++set) for (uint32_t x = 0; x < P.nxf; ++x) for (uint32_t idx = 0; idx < R; ++idx)
-        tables[((size_t)set * P.nxf + x) * R + idx] = idx ? P.tw[table_entry_exponent(P, x, set, idx)] : make_uint4(0, 0, 0, 0);
-    std::vector<uint4> tile(kTileChunks);
-    uint2* t2 = reinterpret_cast<uint2*>(tile.data());
-    std::vector<RoundRegs> regs(kThreads);
-    std::vector<WarpAddr> wa(kThreads);
-    for (uint32_t tid = 0; tid < kThreads; ++tid) wa[tid] = warp_addr(LR, warp_pos(LR, tid));
-    const uint2* src2 = reinterpret_cast<const uint2*>(P.src);
-    uint2* dst2 = reinterpret_cast<uint2*>(P.dst);
-    const bool two = LR > (uint32_t)kStages;
-    for (uint32_t set = 0; set < P.nsets; ++set) {
-        const uint4* tw0 = tables.data() + (size_t)(nst > 1 ? set : 0) * P.nxf * R;
-        const uint4* tw1 = tw0 + R;
-        for (uint32_t strip = 0; strip < P.nstrips; ++strip) {
-            for (uint32_t row = 0; row < R; ++row) for (uint32_t q2 = 0; q2 < Wt / 2; ++q2) {          // TMA load, OOB -> 0
-                const uint32_t g2 = strip * (Wt / 2) + q2;
-                const size_t grow = (size_t)set * P.src_set_stride + (size_t)row * P.src_row_stride;
-                t2[cell8(LR, row, q2)] = (g2 >> 1) < P.s4 ? src2[grow * P.pitch4 * 2 + g2] : make_uint2(0, 0);
-            }
-            auto run = [&](int ph) {
-                for (uint32_t tid = 0; tid < kThreads; ++tid)
-                    if (warp_col_active(P, warp_pos(LR, tid), strip)) warp_phase(P, ph, tid, set, wa[tid], tile.data(), tw0, tw1, regs[tid], 0);
-            };
-            run(0); run(1);
-            if (two) { run(2); run(3); run(4); if (P.nxf == 2) { run(5); run(6); run(7); } }
-            run(8);
-            for (uint32_t row = 0; row < R; ++row) for (uint32_t q2 = 0; q2 < Wt / 2; ++q2) {          // TMA store, clipped
-                const uint32_t g2 = strip * (Wt / 2) + q2;
-                if ((g2 >> 1) >= P.s4) continue;
-                const size_t grow = (size_t)set * P.dst_set_stride + (size_t)row * P.dst_row_stride;
-                dst2[grow * P.pitch4 * 2 + g2] = t2[cell8(LR, row, q2)];
-            }
-        }
-    }
-}

@@ -11,7 +11,6 @@
 #include "gfp_oracle.h"
 
 static std::vector<gf::Tw> g_tw;
-static bool g_warp = false;
 
 static int check(const char* what, size_t N, size_t S, int mode /*0 fwd,1 inv,2 encode*/)
 {
@@ -21,7 +20,7 @@ static int check(const char* what, size_t N, size_t S, int mode /*0 fwd,1 inv,2 
     for (size_t i = 0; i < N; i++) memcpy(&x[i * pitch], &ref[i * S], S * 4);
     Buffers b{x.data(), y.data(), reinterpret_cast<const uint4*>(g_tw.data()), (uint32_t)pitch, (uint32_t)S};
     std::vector<PassParams> plan = (mode == 2) ? plan_encode(b, N) : plan_ntt(b, N, mode == 1);
-    for (auto& p : plan) { if (g_warp) emulate_pass_warp(p); else emulate_pass(p); }
+    for (auto& p : plan) emulate_pass(p);
     if (mode == 2) oracle_rs_encode(ref.data(), N, S); else oracle_ntt(ref.data(), N, S, mode);
     size_t bad = 0;
     for (size_t i = 0; i < N; i++) for (size_t k = 0; k < S; k++) if (x[i * pitch + k] != ref[i * S + k]) { if (!bad) printf("   first mismatch row %zu word %zu: got %u want %u\n", i, k, x[i*pitch+k], ref[i*S+k]); bad++; }
@@ -35,7 +34,6 @@ int main(int argc, char** argv)
     fill_power_table(g_tw.data());
     int fails = 0;
     const bool big = argc > 1 && !strcmp(argv[1], "big");
-    for (int a = 1; a < argc; ++a) if (!strcmp(argv[a], "warp")) g_warp = true;
     struct Cfg { unsigned ln; size_t s; };
     std::vector<Cfg> cfgs = { {5, 8}, {5, 1024}, {6, 1024}, {7, 1024}, {8, 20}, {9, 36}, {10, 16}, {10, 24}, {11, 16}, {12, 8}, {13, 4}, {7, 513} };
     if (big) { cfgs.push_back({16, 16}); cfgs.push_back({19, 16}); cfgs.push_back({20, 4}); cfgs.push_back({15, 32}); }
