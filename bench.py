@@ -1,11 +1,16 @@
 #!/usr/bin/env python
 """bench.py -- RS encode GB/s at (n,k)=(2^20,2^19), 4 KiB blocks (BASELINE.json metric), on N B200s.
 
-Own arm (default): one process per GPU (torchrun for N>1).  A step = one full encode (RS.cpp:41-63) of
-N=2^19 data blocks x 4096 B resident in HBM -> 2^19 parity blocks, through the C ABI
-(fastecc_b200_rs_encode_dev).  Throughput convention is the reference's: bytes = 2*N*SIZE*4 per encode
-(RS.cpp:38).  With N>1 GPUs every rank encodes its own independent stripe of 2^19 blocks (weak scaling, no
-data-path collective).
+Own arm (default): one process per GPU (torchrun for N>1).  A step = one full encode (RS.cpp:41-63) of N=2^19 data
+blocks x 4096 B -> 2^19 parity blocks.  Throughput convention is the reference's: bytes = 2*N*SIZE*4 per encode (RS.cpp:38).
+  N = 1: the array is resident in HBM, the step is fastecc_b200_rs_encode_dev (three pass kernels).
+  N > 1: ONE encode sharded over the N GPUs (BASELINE config 4; "scaling": "strong"): blocks dealt cyclically, the
+         four-step transposes (TransposeMatrix, ntt.cpp:322-341,415,433,445) fused into the pass kernels' stores over
+         peer memory (fastecc_b200/sharded.py).  Independent stripes per GPU (no data-path collective, weak scaling) are
+         reported as the secondary block "stripes" of the same line.
+Before anything is timed the result is checked: the parity of the reference's own fill (data0[i] = i % P, RS.cpp:28-29)
+must hash (main.cpp:203-212) to the golden value of the unmodified reference, and for N > 1 the gathered sharded result
+must equal the single-GPU encode bit for bit.  A mismatch aborts the run: no line is printed.
 
 `--impl reference`: times the UNMODIFIED reference CPU encoder (oracle/_ref, compiled from /root/reference by
 oracle/Makefile: AVX2 + OpenMP build, all host threads) on the same config; rank 0 only.
@@ -26,6 +31,41 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 P = 0xFFF00001
 METRIC = "rs_encode_GBps_n2^20_k2^19_4KiB_blocks"
+# hash (main.cpp:203-212) of the parity of fill A (data0[i] = i % P), recorded from the unmodified reference: SURVEY.md 8c,
+# tests/golden/survey_8c.json "encode_fillA"; key = (log2 N, words per block)
+GOLDEN_PARITY_HASH_FILL_A = {(7, 1024): 421122310, (11, 1024): 2634925848, (16, 1024): 147925734, (19, 1024): 4272226309, (7, 513): 56723226}
+
+
+def workload_name(args):
+    """The same string in both arms (the driver compares it); where the data lives is config.residency."""
+    return "rs_encode N=2^%d data blocks -> 2^%d parity, %d-byte blocks, GF(0xFFF00001)" % (args.log_n, args.log_n, args.block_bytes)
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Run this process (and therefore its pinned allocations: first touch) on the CPUs of the NUMA node the GPU hangs off.
+    Returns a short description; never fails."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:                 # nvml prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return "numa node unknown"
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "numa node %d has no allowed cpu" % node
+        os.sched_setaffinity(0, cpus)
+        return "numa node %d (%d cpus)" % (node, len(cpus))
+    except Exception as e:                              # noqa: BLE001 -- binding is an optimisation
+        return "not bound (%s)" % type(e).__name__
 
 
 def profiled_traffic():
@@ -63,8 +103,10 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--mode", default="stripes", choices=["stripes", "sharded", "sharded-a2a"],
-                    help="multi-GPU: independent stripe per GPU (default, weak scaling) or ONE transform sharded over the GPUs with two NCCL all-to-alls (strong scaling, BASELINE config 4)")
+    ap.add_argument("--mode", default="sharded", choices=["sharded", "sharded-a2a", "stripes"],
+                    help="multi-GPU headline: ONE transform sharded over the GPUs with the exchange fused into the kernels' stores (default; strong scaling, "
+                         "BASELINE config 4), the same with two NCCL all-to-alls, or only independent stripes (weak scaling)")
+    ap.add_argument("--no-stripes", action="store_true", help="skip the secondary independent-stripes measurement of a multi-GPU run")
     return ap.parse_args()
 
 
@@ -221,8 +263,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup,
         "ms_per_step": 1e3 * total / len(times), "best_ms": 1e3 * min(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
-        "config": {"workload": "rs_encode N=2^%d data blocks -> 2^%d parity, %d-byte blocks, GF(0xFFF00001), host memory" % (args.log_n, args.log_n, args.block_bytes),
-                   "bytes_per_step": nbytes, "convention": "2*N*SIZE*4 bytes per encode (RS.cpp:38)"},
+        "config": {"workload": workload_name(args), "residency": "host memory", "bytes_per_step": nbytes, "convention": "2*N*SIZE*4 bytes per encode (RS.cpp:38)"},
         "cpu_baseline": {"value": value, "unit": "GB/s", "cores": cores, "kind": kind, "sample": "%d full encodes of the workload; %s" % (len(times), label)},
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -251,6 +292,49 @@ def quick_cpu_baseline(args):
 
 
 # ---------------------------------------------------------------------------------------------------- B200 arm
+def fill_a_rows(torch, dev, first_row, row_step, rows, S):
+    """Rows first_row + l*row_step (l < rows) of the reference's fill data0[i] = i % P (RS.cpp:28-29) as an int32 CUDA tensor."""
+    out = torch.empty((rows, S), dtype=torch.int32, device=dev)
+    cols = torch.arange(S, device=dev, dtype=torch.int64)
+    step = max(1, (1 << 24) // S)
+    for lo in range(0, rows, step):
+        hi = min(lo + step, rows)
+        r = (torch.arange(lo, hi, device=dev, dtype=torch.int64) * row_step + first_row) * S
+        out[lo:hi] = ((r[:, None] + cols[None, :]) % P).to(torch.int32)
+    return out
+
+
+def parity_hash(fe, t):
+    """main.cpp:203-212 over the blocks of a device tensor, through the library's fastecc_b200_hash_u32."""
+    import numpy as np
+    return fe.reference_hash(t.cpu().numpy().view(np.uint32))
+
+
+def check_golden(args, h, what):
+    key = (args.log_n, args.block_bytes // 4)
+    want = GOLDEN_PARITY_HASH_FILL_A.get(key) if args.block_bytes % 4 == 0 else None
+    if want is not None and h != want:
+        raise SystemExit("PARITY FAILURE (%s): hash %d != golden %d of the unmodified reference for N=2^%d, %d-byte blocks" % (what, h, want, key[0], args.block_bytes))
+    return {"hash": h, "golden": want, "golden_match": None if want is None else True}
+
+
+def per_kernel_roofline(fe, data, nbytes, peak, reps):
+    """Per pass kernel: average duration over `reps` encodes with CUDA events between the launches (a separate loop right after
+    the timed region: fastecc_b200_rs_encode_dev_timed synchronises the stream), algorithmic bytes = one read + one write of the array."""
+    acc = None
+    for _ in range(reps):
+        t = fe.rs_encode_dev_timed(data)
+        acc = [[n, ms] for n, ms in t] if acc is None else [[a[0], a[1] + ms] for a, (_, ms) in zip(acc, t)]
+    acc = acc or []
+    labels = {1: ["fused"], 2: ["A'", "B'"], 3: ["A", "BC", "D"]}.get(len(acc), [str(i) for i in range(len(acc))])
+    out = []
+    for lab, (name, ms) in zip(labels, acc):
+        ms /= reps
+        ach = nbytes / (ms * 1e-3) / 1e9
+        out.append({"pass": lab, "kernel": name, "ms": round(ms, 4), "achieved": round(ach, 1), "frac": round(ach / peak, 4)})
+    return out
+
+
 def run_b200_arm(args):
     import numpy as np
     import torch
@@ -259,6 +343,7 @@ def run_b200_arm(args):
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    numa = bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -270,28 +355,24 @@ def run_b200_arm(args):
     N, S = 1 << args.log_n, args.block_bytes // 4
     dev = torch.device("cuda", local)
     if args.mode in ("sharded", "sharded-a2a") and world > 1:
-        return run_sharded(args, fe, rank, world, local, dev)
-    data = torch.empty((N, S), dtype=torch.int32, device=dev)
-    flat = data.view(-1)
-    step_elems = 1 << 26
-    for lo in range(0, flat.numel(), step_elems):                      # fill A: data0[i] = i % P  (RS.cpp:28-29)
-        hi = min(lo + step_elems, flat.numel())
-        flat[lo:hi] = (torch.arange(lo, hi, device=dev, dtype=torch.int64) % P).to(torch.int32)
-    nbytes = 2.0 * N * S * 4
+        return run_sharded(args, fe, rank, world, local, dev, numa)
+    return run_single_or_stripes(args, fe, rank, world, local, dev, numa)
+
+
+def time_stripes(args, fe, dev, world, data):
+    """K encodes of this rank's own HBM-resident stripe between CUDA events; max over ranks.  Returns (ms, launches)."""
+    import torch
+    import torch.distributed as dist
+    from fastecc_b200 import multirank
 
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-
     for _ in range(max(args.warmup, 3)):
         fe.rs_encode_dev(data)
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-        time.sleep(0.25)
     launches0 = fe.kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -300,12 +381,43 @@ def run_b200_arm(args):
         fe.rs_encode_dev(data)
     ev1.record()
     torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1)
+    ms = multirank.max_over_ranks(ev0.elapsed_time(ev1), device=dev)          # a multi-GPU step takes as long as its slowest rank
     launches = fe.kernel_launches() - launches0
-    clocks = sampler.stop() if sampler else None
-    from fastecc_b200 import multirank
-    ms = multirank.max_over_ranks(ms, device=dev)          # a multi-GPU step takes as long as its slowest rank
     barrier()
+    return ms, launches
+
+
+def run_single_or_stripes(args, fe, rank, world, local, dev, numa):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from fastecc_b200 import multirank
+    N, S = 1 << args.log_n, args.block_bytes // 4
+    nbytes = 2.0 * N * S * 4
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- parity first: the reference's own fill must give the reference's parity hash
+    data = fill_a_rows(torch, dev, 0, 1, N, S)
+    fe.rs_encode_dev(data)
+    parity = {"device_resident": check_golden(args, parity_hash(fe, data), "device-resident encode")} if rank == 0 else None
+    want_dev = data if not args.no_e2e else None                          # kept to compare the end-to-end result with
+    data = fill_a_rows(torch, dev, 0, 1, N, S)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.25)
+    ms, launches = time_stripes(args, fe, dev, world, data)
+    clocks = sampler.stop() if sampler else None
+
+    peak, peak_src = measured_peak()
+    kernels = per_kernel_roofline(fe, data, nbytes, peak, max(3, min(args.steps, 10))) if rank == 0 else None
+    del data
 
     # ---- end-to-end through the reference-facing host call (T** table, pinned host memory, H2D + D2H inside)
     e2e = None
@@ -315,7 +427,15 @@ def run_b200_arm(args):
             raise SystemExit("pinned allocation failed")
         harr = np.ctypeslib.as_array((ctypes.c_uint32 * (N * S)).from_address(hptr)).reshape(N, S)
         fill_index_mod_p(harr)
-        fe.EncodeReedSolomon_body(harr, N, S)                           # warm-up (allocates the device staging buffer)
+        fe.EncodeReedSolomon_body(harr, N, S)                           # warm-up (allocates the device staging buffer) ...
+        same = bool(torch.equal(torch.from_numpy(harr.view(np.int32)), want_dev.cpu()))       # ... and the parity check of this path
+        if not same:
+            raise SystemExit("PARITY FAILURE: fastecc_b200_rs_encode (host T** path) differs from the device-resident encode")
+        if rank == 0:
+            parity["host_api"] = dict(check_golden(args, fe.reference_hash(harr), "host T** encode"), equals_device_resident=True)
+        del want_dev
+        torch.cuda.empty_cache()
+        fill_index_mod_p(harr)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
@@ -324,29 +444,30 @@ def run_b200_arm(args):
         e2e_s = time.perf_counter() - t0
         e2e_s = multirank.max_over_ranks(e2e_s, device=dev)
         e2e = {"value": world * nbytes * args.e2e_steps / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": N * S * 4, "d2h_bytes_per_step": N * S * 4,
-               "ms_per_step": 1e3 * e2e_s / args.e2e_steps, "api": "fastecc_b200_rs_encode(T** data, N, SIZE) on pinned host blocks"}
+               "ms_per_step": 1e3 * e2e_s / args.e2e_steps, "api": "fastecc_b200_rs_encode(T** data, N, SIZE) on pinned host blocks", "host_numa": numa}
         del harr
         fe.lib().fastecc_b200_host_free(hptr)
 
     if rank == 0:
-        peak, peak_src = measured_peak()
         traffic, traffic_src = profiled_traffic() if (args.log_n == 19 and args.block_bytes == 4096) else (None, None)
-        passes_per_step = launches / max(args.steps, 1)
-        launch_ms = ms / max(launches, 1)
-        achieved = nbytes / (launch_ms * 1e-3) / 1e9              # every pass reads and writes the whole array once
+        top = max(kernels, key=lambda k: k["ms"]) if kernels else {"kernel": "small_dft_kernel", "pass": "single", "achieved": nbytes / (ms / args.steps * 1e-3) / 1e9,
+                                                                   "frac": nbytes / (ms / args.steps * 1e-3) / 1e9 / peak}
         out = {
             "metric": METRIC, "value": world * nbytes * args.steps / (ms * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
-            "config": {"workload": "rs_encode N=2^%d data blocks -> 2^%d parity, %d-byte blocks, GF(0xFFF00001), resident in HBM" % (args.log_n, args.log_n, args.block_bytes),
+            "config": {"workload": workload_name(args), "residency": "HBM (value) / pinned host memory (e2e)",
                        "bytes_per_step": nbytes, "convention": "2*N*SIZE*4 bytes per encode (RS.cpp:38)", "per_gpu_buffer_bytes": N * S * 4,
                        "l2": "inputs (2 GiB per GPU) are larger than L2; no flush needed", "parallelism": "independent stripe per GPU" if world > 1 else "single GPU",
-                       "passes_per_encode": passes_per_step},
-            "roofline": {"bound": "hbm", "kernel": "ntt_pass_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "note": "algorithmic bytes per launch = 2*N*SIZE*4 (one read + one write of the array per pass); avg launch = timed region / launches"},
+                       "passes_per_encode": launches / max(args.steps, 1)},
+            "roofline": {"bound": "hbm", "kernel": top["kernel"], "pass": top["pass"], "achieved": top["achieved"], "peak": peak, "unit": "GB/s", "frac": top["frac"],
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "per_kernel": kernels,
+                         "encode_frac_of_compulsory_bytes": round(nbytes / (ms / args.steps * 1e-3) / 1e9 / peak, 4),
+                         "note": "dominant (longest) pass kernel; algorithmic bytes per launch = 2*N*SIZE*4 (one read + one write of the array per pass); "
+                                 "durations = CUDA events between the launches, averaged over a loop of encodes right after the timed region"},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "parity": parity,
         }
         if e2e:
             out["e2e"] = e2e
@@ -358,23 +479,26 @@ def run_b200_arm(args):
     return 0
 
 
-def run_sharded(args, fe, rank, world, local, dev):
-    """ONE encode of 2^log_n blocks sharded over the ranks: local passes + two all-to-alls (fastecc_b200/sharded.py)."""
+def run_sharded(args, fe, rank, world, local, dev, numa):
+    """ONE encode of 2^log_n blocks sharded over the ranks (fastecc_b200/sharded.py): parity check, device-resident timing,
+    per-phase times, end to end from pinned host shards, and the independent-stripes figure as a secondary block."""
+    import numpy as np
     import torch
     import torch.distributed as dist
     from fastecc_b200 import multirank, sharded
     N, S = 1 << args.log_n, args.block_bytes // 4
     rows = N // world
-    x = (torch.arange(rows * S, device=dev, dtype=torch.int64) * 2654435761 % P).to(torch.int32).view(rows, S)
     nbytes = 2.0 * N * S * 4
     fused = args.mode == "sharded" and sharded.p2p_supported(N, world)
     if fused:                                   # exchange fused into the kernels' stores over peer memory
         enc = sharded.P2PShardedEncoder(N, S)
-        enc.x.copy_(x)
 
-        def step(_):
+        def step(t):
+            if t is not enc.x:
+                enc.x.copy_(t)
             return enc.encode()
     else:                                       # local passes + two NCCL all-to-alls
+        enc = None
         run_pass = sharded.gpu_pass_runner(N, world, rank)
 
         def step(t):
@@ -383,6 +507,28 @@ def run_sharded(args, fe, rank, world, local, dev):
     def sync():
         torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
 
+    # ---- parity first.  Global block l*G + rank is local row l; fill A = data0[i] = i % P over the GLOBAL array (RS.cpp:28-29).
+    mine = step(fill_a_rows(torch, dev, rank, world, rows, S)).clone()
+    gathered = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+    dist.gather(mine, gathered, dst=0)
+    parity = None
+    if rank == 0:
+        par = torch.empty((N, S), dtype=torch.int32, device=dev)
+        for r in range(world):
+            par[r::world] = gathered[r]
+        gathered = None
+        single = fill_a_rows(torch, dev, 0, 1, N, S)
+        fe.rs_encode_dev(single)                                        # the single-GPU encode of the same array
+        same = bool(torch.equal(par, single))
+        del single
+        if not same:
+            raise SystemExit("PARITY FAILURE: the sharded encode over %d GPUs differs from the single-GPU encode" % world)
+        parity = {"sharded": dict(check_golden(args, parity_hash(fe, par), "sharded encode"), equals_single_gpu_encode=True)}
+        del par
+        torch.cuda.empty_cache()
+    sync()
+
+    x = fill_a_rows(torch, dev, rank, world, rows, S)
     for _ in range(max(args.warmup, 3)):
         x = step(x)
     sync()
@@ -402,31 +548,86 @@ def run_sharded(args, fe, rank, world, local, dev):
     clocks = sampler.stop() if sampler else None
     sync()
     phases = None
-    if fused:                                   # one more encode with events between the phases (rank 0's view)
-        evs = []
-        enc.encode(events=evs)
-        torch.cuda.synchronize()
-        phases = dict(zip(["pass_A", "barrier_1", "pass_BC", "barrier_2", "pass_D"], [round(evs[i].elapsed_time(evs[i + 1]), 4) for i in range(5)]))
+    if fused:                                   # more encodes with events between the phases (max over ranks of the mean per phase)
+        names = ["pass_A", "barrier_1", "pass_BC", "barrier_2", "pass_D"]
+        acc = [0.0] * 5
+        reps = 5
+        for _ in range(reps):
+            evs = []
+            enc.encode(events=evs)
+            torch.cuda.synchronize()
+            for i in range(5):
+                acc[i] += evs[i].elapsed_time(evs[i + 1]) / reps
+            sync()
+        phases = {n: round(multirank.max_over_ranks(v, device=dev), 4) for n, v in zip(names, acc)}
+
+    # ---- end to end: every rank holds its shard in pinned host memory (allocated on its GPU's NUMA node)
+    e2e = None
+    if fused and not args.no_e2e:
+        hptr = fe.lib().fastecc_b200_host_alloc(rows * S * 4)
+        if not hptr:
+            raise SystemExit("pinned allocation failed")
+        harr = np.ctypeslib.as_array((ctypes.c_uint32 * (rows * S)).from_address(hptr)).reshape(rows, S)
+        shard_cpu = fill_a_rows(torch, dev, rank, world, rows, S).cpu().numpy().view(np.uint32)
+        harr[:] = shard_cpu
+        enc.encode_host(harr)                                           # warm-up and parity check of this path
+        ok = torch.tensor([1 if bool(torch.equal(torch.from_numpy(harr.view(np.int32)), mine.cpu())) else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) != 1:
+            raise SystemExit("PARITY FAILURE: sharded encode_host (pinned host shards) differs from the device-resident sharded encode")
+        if rank == 0:
+            parity["sharded_host_api"] = {"equals_device_resident_sharded": True}
+        harr[:] = shard_cpu
         sync()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            enc.encode_host(harr)
+        torch.cuda.synchronize()
+        e2e_s = multirank.max_over_ranks(time.perf_counter() - t0, device=dev)
+        e2e = {"value": nbytes * args.e2e_steps / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": N * S * 4, "d2h_bytes_per_step": N * S * 4,
+               "ms_per_step": 1e3 * e2e_s / args.e2e_steps, "host_numa_rank0": numa,
+               "api": "P2PShardedEncoder.encode_host: every rank's N/G blocks in pinned host memory, column-chunked H2D / 3 sharded passes / D2H pipeline; bytes are the totals over all ranks"}
+        del harr, shard_cpu
+        fe.lib().fastecc_b200_host_free(hptr)
+        sync()
+    del mine
+
+    # ---- secondary: independent stripes (one full 2^log_n encode per GPU, no data-path collective)
+    stripes = None
+    if not args.no_stripes:
+        data = fill_a_rows(torch, dev, 0, 1, N, S)
+        sms, _ = time_stripes(args, fe, dev, world, data)
+        del data
+        stripes = {"value": world * nbytes * args.steps / (sms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": sms / args.steps, "scaling": "weak",
+                   "what": "every GPU encodes its own independent 2^%d-block stripe (communication-free row of SURVEY 8e); aggregate over %d GPUs" % (args.log_n, world)}
+
     if rank == 0:
-        a2a_bytes = 2.0 * (world - 1) / world * (N * S * 4 / world)           # sent per GPU per encode (two all-to-alls)
+        a2a_bytes = 2.0 * (world - 1) / world * (N * S * 4 / world)           # sent per GPU per encode (two exchanges)
         link = 770.0                                                          # GB/s per direction per GPU, measured peer copy (B200_PROFILING.md)
         t_link = a2a_bytes / (link * 1e9)
+        step_s = ms / args.steps * 1e-3
         out = {
-            "metric": METRIC, "value": nbytes * args.steps / (ms * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC, "value": nbytes / step_s / 1e9, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
-            "config": {"workload": "rs_encode N=2^%d data blocks -> 2^%d parity, %d-byte blocks, ONE transform sharded over %d GPUs" % (args.log_n, args.log_n, args.block_bytes, world),
-                       "bytes_per_step": nbytes, "convention": "2*N*SIZE*4 bytes per encode (RS.cpp:38)", "parallelism": ("cyclic blocks, 3 passes; passes A and BC store every output row into its owner's HBM over NVLink (peer-mapped, CUDA IPC), 2 one-word all-reduce barriers"
-                                       if fused else "cyclic blocks, 3 local passes + 2 NCCL all-to-all"),
+            "config": {"workload": workload_name(args), "residency": "HBM, N/G blocks per GPU (value) / pinned host shards (e2e)",
+                       "bytes_per_step": nbytes, "convention": "2*N*SIZE*4 bytes per encode (RS.cpp:38)",
+                       "parallelism": ("ONE transform over %d GPUs: cyclic blocks, 3 passes; passes A and BC store every output row into its owner's HBM over NVLink "
+                                       "(peer-mapped, CUDA IPC), 2 one-word all-reduce barriers" % world
+                                       if fused else "ONE transform over %d GPUs: cyclic blocks, 3 local passes + 2 NCCL all-to-all" % world),
                        "l2": "local arrays (%.0f MiB per GPU) exceed L2" % (N * S * 4 / world / 2**20)},
-            "roofline": {"bound": "nvlink", "achieved": a2a_bytes / (ms / args.steps * 1e-3) / 1e9, "peak": link, "unit": "GB/s",
-                         "frac": t_link / (ms / args.steps * 1e-3), "traffic": None,
+            "roofline": {"bound": "nvlink", "kernel": "ntt_pass_dual_kernel<9,1> (A) + ntt_pass_kernel<10,2,2> (BC): sharded-store instantiations",
+                         "achieved": a2a_bytes / step_s / 1e9, "peak": link, "unit": "GB/s",
+                         "frac": t_link / step_s, "traffic": None,
                          "note": "bytes each GPU sends to its peers per encode (2 exchanges of (G-1)/G of the local array) / step time, against the measured 770 GB/s per-direction peer bandwidth"},
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
         }
         if phases:
-            out["phases_ms_rank0"] = phases
+            out["phases_ms_max_over_ranks"] = phases
+        if e2e:
+            out["e2e"] = e2e
+        if stripes:
+            out["stripes"] = stripes
         emit(out)
     if fused:
         enc.close()

@@ -82,17 +82,20 @@ GF_HD void wp_bits(uint32_t whi, uint32_t wlo, uint32_t& lo, uint32_t& hi)
     const uint64_t bits = ((uint64_t)(1022u - lz) << 52) | ((m >> 11) & ((1ull << 52) - 1));      // truncation = round down
     lo = (uint32_t)bits; hi = (uint32_t)(bits >> 32);
 }
+#if defined(FECC_CVT_MAGIC)
+#define FECC_CVT_DEFAULT 1
+#else
+#define FECC_CVT_DEFAULT 0
+#endif
+template <int CVT = FECC_CVT_DEFAULT>     // 0: I2F.F64.U32 (XU pipe); 1 (experiment): {b, 0x43300000} - 2^52 on the FP64 unit
 GF_HD uint32_t mul_h(uint32_t b, uint32_t w, uint32_t wplo, uint32_t wphi)
 {
     uint32_t q;
 #if defined(__CUDA_ARCH__)
     double bd, qd;
     const double wp = __hiloint2double((int)wphi, (int)wplo);
-#if defined(FECC_CVT_MAGIC)      // experiment: {b, 0x43300000} - 2^52 on the FP64 unit instead of I2F on the XU pipe
-    asm("{\n\t.reg .f64 t;\n\tmov.b64 t, {%1, %2};\n\tsub.rn.f64 %0, t, 0d4330000000000000;\n\t}" : "=d"(bd) : "r"(b), "r"(0x43300000u));
-#else
-    asm("cvt.rn.f64.u32 %0, %1;" : "=d"(bd) : "r"(b));
-#endif
+    if (CVT == 1) asm("{\n\t.reg .f64 t;\n\tmov.b64 t, {%1, %2};\n\tsub.rn.f64 %0, t, 0d4330000000000000;\n\t}" : "=d"(bd) : "r"(b), "r"(0x43300000u));
+    else          asm("cvt.rn.f64.u32 %0, %1;" : "=d"(bd) : "r"(b));
     asm("fma.rm.f64 %0, %1, %2, 0d4330000000000000;" : "=d"(qd) : "d"(bd), "d"(wp));
     q = (uint32_t)__double2loint(qd);
 #else

@@ -12,7 +12,7 @@
 //   * ceil(LR/5) <= 2 register rounds of up to five radix-2 stages (three for a fused two-transform tile, whose
 //     middle round runs 4+5 stages back to back in registers) separated by one block barrier each;
 //   * 64-bit stores of the finished rows straight from registers.
-// The kernel is bound by the integer multiply pipe (IMAD.HI on "fmaheavy"), not by HBM: see profiles/.
+// The kernel is bound by instruction issue (XU conversions + FP64 / integer multiplies + the lazy add/sub), not by HBM: see profiles/.
 #include "ntt_tile.cuh"
 #include "ntt_pass.h"
 #include "plan.h"
@@ -180,116 +180,6 @@ __global__ void __launch_bounds__(kThreads, 2) ntt_pass_kernel(const PassParams 
 }
 
 
-__device__ __forceinline__ void group_sync(uint32_t g) { asm volatile("bar.sync %0, %1;" :: "r"(g + 1u), "r"((uint32_t)kThreads) : "memory"); }
-
-// "Dual" schedule for single-transform passes (A, D, A', B'): ONE 512-thread CTA per SM = two groups of 256 threads
-// that each run the CTA-level tile schedule of ntt_pass_kernel on alternate tiles of the CTA's sequence, sharing a pool
-// of THREE tile buffers.  Tile k lives in buffer k % 3; when the group working on tile k has lifted it into registers
-// for its last round, the buffer is free and the group's thread 0 requests tile k+3 (the OTHER group's tile after
-// next) into it.  A tile's load therefore has a whole tile period of the other group to land, instead of the half
-// period a CTA of ntt_pass_kernel can offer with its single buffer: the strided passes are balanced between DRAM
-// (0.85 ms copy-only) and butterflies (~0.9 ms), so hiding one behind the other is what they need.
-// Stage tables: a set-independent table is loaded once; otherwise each group double-buffers its own (slot 2g + parity),
-// requested one tile ahead by the group itself.
-template <int LR, int SHARD>
-__global__ void __launch_bounds__(2 * kThreads, 1) ntt_pass_dual_kernel(const PassParams Pin, const __grid_constant__ CUtensorMap tmap)
-{
-    PassParams P = Pin;
-    P.log_r = LR; P.nxf = 1; P.use_tma = 1;
-    if (!SHARD) P.log_g = 0;
-    extern __shared__ __align__(1024) uint4 smem[];
-    constexpr uint32_t R = 1u << LR;
-    constexpr uint32_t kBufs = 3;
-    const bool var0 = P.xf[0].t1 != 0;
-    uint4* tabs = smem + kBufs * kTileChunks;                                   // var0 ? [2 groups][2][R] : [R]
-    // full[buffer][use & 1]: the tile of the buffer's use-th fill has landed (parity (use >> 1) & 1).  Two barriers per
-    // buffer because the consumer of fill u+1 is the OTHER group, which may arrive while fill u is still in flight:
-    // on a single barrier its parity wait would be satisfied by fill u-1.
-    uint64_t* full  = reinterpret_cast<uint64_t*>(tabs + (var0 ? 4u : 1u) * R);
-    uint64_t* rbar  = full + 2 * kBufs;                                         // rbar[2]: the group's 8 warps are done reading their tile
-    uint64_t* tfull = rbar + 2;                                                 // tfull[2]: the group's next table has landed ([0] also: the shared table)
-    const uint32_t g = threadIdx.x / kThreads, tid = threadIdx.x % kThreads;
-    const uint32_t groups = (P.nstrips + P.strips_per_item - 1) / P.strips_per_item;
-    const uint32_t nitems = P.nsets * groups;
-    constexpr uint32_t nsteps = LR > kStages ? 2u : 1u;
-    constexpr uint32_t kWt = 16384u >> LR;
-    constexpr uint32_t kRowsBox = R < 256u ? R : 256u;
-    constexpr uint32_t kBoxes = R / kRowsBox;
-
-    if (threadIdx.x == 0) {
-        for (uint32_t b = 0; b < 2 * kBufs; ++b) mbar_init(full + b, 1);
-        mbar_init(rbar, kThreads / 32); mbar_init(rbar + 1, kThreads / 32);
-        mbar_init(tfull, 1); mbar_init(tfull + 1, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-
-    auto request_tile = [&](uint32_t k, uint32_t buf, uint32_t use) {           // one thread
-        uint32_t set, strip;
-        if (!tile_decode(P, groups, nitems, k, set, strip)) return;
-        fence_proxy_async();
-        uint64_t* bar = full + 2 * buf + (use & 1u);
-        mbar_expect_tx(bar, kTileBytes);
-        uint4* dst = smem + buf * kTileChunks;
-#pragma unroll
-        for (uint32_t b = 0; b < kBoxes; ++b)
-            tma_load_3d(dst + b * (kRowsBox * (kWt / 4)), &tmap, bar, strip * kWt, b * kRowsBox, set);
-    };
-    auto request_table = [&](uint32_t k, uint32_t slot, uint64_t* bar) {        // one thread
-        uint32_t set, strip;
-        if (!tile_decode(P, groups, nitems, k, set, strip)) return;
-        fence_proxy_async();
-        mbar_expect_tx(bar, R * 16u);
-        bulk_load(tabs + slot * R, P.tables + (size_t)set * P.table_set_stride, R * 16u, bar);
-    };
-
-    if (threadIdx.x == 0) {
-        if (!var0) request_table(0, 0, tfull);
-        request_tile(0, 0, 0); request_tile(1, 1, 0); request_tile(2, 2, 0);
-    }
-    if (var0 && tid == 0) request_table(g, 2 * g, tfull + g);
-    if (!var0) mbar_wait(tfull, 0);
-
-    uint32_t buf = g, use = 0;                            // tile k = g + 2*j: buffer k % 3, its (k / 3)-th use
-    for (uint32_t k = g, j = 0;; k += 2, ++j) {
-        uint32_t cur_set, cur_strip;
-        if (!tile_decode(P, groups, nitems, k, cur_set, cur_strip)) break;
-        const uint32_t tslot = var0 ? 2 * g + (j & 1u) : 0u;
-        if (var0) mbar_wait(tfull + g, j & 1u);
-        mbar_wait(full + 2 * buf + (use & 1u), (use >> 1) & 1u);
-        uint4* tile = smem + buf * kTileChunks;
-        const uint4* tw0 = tabs + tslot * R;
-        const bool active = thread_active(P, tid, cur_strip);
-        RoundRegs r;
-#pragma unroll 1
-        for (uint32_t s = 0; s < nsteps; ++s) {
-            const Step st = step_of(LR, 1, s);
-            const bool last = s + 1 == nsteps;
-            if (active) round_read(P, st.k, true, tid, tile, r);
-            if (last) {
-                __syncwarp();
-                if ((tid & 31) == 0) mbar_arrive(rbar + g);
-                if (tid == 0) {
-                    mbar_wait(rbar + g, j & 1u);
-                    request_tile(k + 3, buf, use + 1);                          // the other group's tile after next
-                    if (var0) request_table(k + 2, 2 * g + ((j + 1) & 1u), tfull + g);   // our own next table: its slot was last used by tile k-2
-                }
-            }
-            #if !defined(FECC_SKIP_MATH)
-            if (active) round_math(P, st, tid, cur_set, tw0, tw0, r);
-#endif
-            if (!last) {
-                if (active) round_write_tile(P, st.k, true, tid, tile, r);
-                group_sync(g);
-            } else if (active) {
-                round_write_global(P, st, tid, cur_set, cur_strip, r);
-            }
-        }
-        buf += 2; if (buf >= kBufs) buf -= kBufs;
-        use = (k + 2) / 3;
-    }
-}
-
 // One thread per table entry: tables[set][xfi][idx] = g^exponent (entry 0 of every table is unused).
 __global__ void build_tables_kernel(const PassParams P, uint4* out, uint32_t nsets_tab)
 {
@@ -352,23 +242,6 @@ static bool make_tensor_map(const PassParams& P, CUtensorMap* map)
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static size_t dual_smem_bytes(const PassParams& P)
-{
-    return (size_t)3 * kTileBytes + (size_t)(P.xf[0].t1 ? 4 : 1) * ((size_t)16 << P.log_r) + 10 * sizeof(uint64_t);
-}
-template <int LR, int SHARD>
-static cudaError_t launch_dual_inst(const PassParams& P, const CUtensorMap& map, unsigned grid, cudaStream_t stream)
-{
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(ntt_pass_dual_kernel<LR, SHARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    ntt_pass_dual_kernel<LR, SHARD><<<grid, 2 * kThreads, dual_smem_bytes(P), stream>>>(P, map);
-    return cudaGetLastError();
-}
-
 template <int LR, int NXF, int TMA>
 static cudaError_t launch_inst(const PassParams& P, const CUtensorMap& map, unsigned grid, cudaStream_t stream)
 {
@@ -385,11 +258,11 @@ static cudaError_t launch_inst(const PassParams& P, const CUtensorMap& map, unsi
 }
 
 // name of the instantiation a pass is dispatched to, for the per-kernel lines of the benchmark (static storage)
-static const char* kernel_name(bool dual, uint32_t lr, uint32_t a, uint32_t b)
+static const char* kernel_name(uint32_t lr, uint32_t nxf, uint32_t tma)
 {
-    static char names[2][6][3][3][48];
-    char* n = names[dual ? 1 : 0][lr - 5][a][b];
-    if (!n[0]) { if (dual) snprintf(n, 48, "ntt_pass_dual_kernel<%u,%u>", lr, a); else snprintf(n, 48, "ntt_pass_kernel<%u,%u,%u>", lr, a, b); }
+    static char names[6][3][3][40];
+    char* n = names[lr - 5][nxf][tma];
+    if (!n[0]) snprintf(n, 40, "ntt_pass_kernel<%u,%u,%u>", lr, nxf, tma);
     return n;
 }
 
@@ -409,21 +282,7 @@ cudaError_t launch_pass(const PassParams& Pin, int num_sms, cudaStream_t stream,
     static const bool no_tma = getenv("FASTECC_B200_NO_TMA") != nullptr;
     const bool tma = !no_tma && P.log_r >= 6 && make_tensor_map(P, &map);
     if (P.log_g && !tma) return cudaErrorNotSupported;          // sharded stores exist only in the TMA instantiations
-    // single-transform passes with enough tiles to keep both groups of every SM busy: the dual schedule (3 tile buffers / SM)
-    static const bool no_dual = getenv("FASTECC_B200_KERNEL") && !strcmp(getenv("FASTECC_B200_KERNEL"), "cta");
-    if (tma && !no_dual && P.nxf == 1 && dual_smem_bytes(P) <= 232448 && nitems * P.strips_per_item >= 4ull * num_sms) {
-        const unsigned gd = (unsigned)((unsigned long long)num_sms < nitems ? (unsigned long long)num_sms : nitems);
-        if (kernel) *kernel = kernel_name(true, P.log_r, P.log_g ? 1 : 0, 0);
-        switch (P.log_r) {
-            case 6: return P.log_g ? launch_dual_inst<6, 1>(P, map, gd, stream) : launch_dual_inst<6, 0>(P, map, gd, stream);
-            case 7: return P.log_g ? launch_dual_inst<7, 1>(P, map, gd, stream) : launch_dual_inst<7, 0>(P, map, gd, stream);
-            case 8: return P.log_g ? launch_dual_inst<8, 1>(P, map, gd, stream) : launch_dual_inst<8, 0>(P, map, gd, stream);
-            case 9: return P.log_g ? launch_dual_inst<9, 1>(P, map, gd, stream) : launch_dual_inst<9, 0>(P, map, gd, stream);
-            case 10: return P.log_g ? launch_dual_inst<10, 1>(P, map, gd, stream) : launch_dual_inst<10, 0>(P, map, gd, stream);
-            default: break;
-        }
-    }
-    if (kernel) *kernel = kernel_name(false, P.log_r, P.nxf, tma ? (P.log_g ? 2 : 1) : 0);
+    if (kernel) *kernel = kernel_name(P.log_r, P.nxf, tma ? (P.log_g ? 2 : 1) : 0);
 #define FECC_CASE(L) case L: \
         if (tma && P.log_g) return P.nxf == 2 ? launch_inst<L, 2, 2>(P, map, g, stream) : launch_inst<L, 1, 2>(P, map, g, stream); \
         if (tma) return P.nxf == 2 ? launch_inst<L, 2, 1>(P, map, g, stream) : launch_inst<L, 1, 1>(P, map, g, stream); \

@@ -342,6 +342,9 @@ FECC_HD bool thread_active(const PassParams& P, uint32_t tid, uint32_t strip)
 
 // Tile address (in uint2 units) of the thread's slot i in round c:  physical row = bitrev(slot) for the first
 // transform of a tile (brev), = slot for the second.  Both reduce to "base + i*step" with compile-time i.
+// (Tiles of 1024 rows have 64-byte rows and every shared-memory access of theirs is a 2-way bank conflict; the
+// parity row swap that removes the conflicts was measured and is NOT used: it needs a block barrier between the first
+// read and the first write of a tile, and the fused pass got 5 % slower with it -- DESIGN.md section 12.)
 #define FECC_SLOT_LOOP(ACCESS)                                                                                     \
     if (brev) {                                                                                                    \
         uint32_t a = (bitrev(c.jbase, LR) << tp.q2log) | tp.q2;                                                    \

@@ -147,38 +147,82 @@ class P2PShardedEncoder:
                     fe._check(L.fastecc_b200_ipc_open(everyone[r, k].ctypes.data, ctypes.byref(p)))
                     peers[k][r] = p.value
                     self._opened.append(p.value)
-        self._xp = (ctypes.c_void_p * self.G)(*peers[0])
-        self._yp = (ctypes.c_void_p * self.G)(*peers[1])
+        self._peers = peers                                            # [X or Y][rank] -> device address in this process
+        self._ptr_cache = {}
         self.x = torch.as_tensor(_RawCudaBuffer(self._own[0], (rows, S)), device=torch.device("cuda", self._dev))
         self._flag = torch.zeros(1, dtype=torch.int32, device=self.x.device)
+        self._s_h2d = self._s_d2h = None
         self._barrier()                                                # nobody stores into a peer before everybody has mapped everything
 
     def _barrier(self):
         import torch.distributed as dist
         dist.all_reduce(self._flag, group=self.group)                  # on the current stream: orders the passes of all ranks
 
-    def encode(self, events=None):
-        """events: optional list that receives 6 CUDA events bracketing pass A, barrier, pass BC, barrier, pass D."""
+    def _peer_arrays(self, off_bytes: int):
+        """HOST arrays of the peers' X and Y addresses, shifted to a column offset (column chunks are independent codewords)."""
+        import ctypes
+        if off_bytes not in self._ptr_cache:
+            self._ptr_cache[off_bytes] = tuple((ctypes.c_void_p * self.G)(*[p + off_bytes for p in self._peers[k]]) for k in range(2))
+        return self._ptr_cache[off_bytes]
+
+    def _passes(self, col0: int, width: int, events=None):
+        """The three passes on word columns [col0, col0 + width) of every block, on the current stream."""
         import torch
         import fastecc_b200 as fe
         L, st = self._lib, torch.cuda.current_stream().cuda_stream
-        X, Y = self._own
+        X, Y = self._own[0] + 4 * col0, self._own[1] + 4 * col0
+        xp, yp = self._peer_arrays(4 * col0)
 
         def mark():
             if events is not None:
                 e = torch.cuda.Event(enable_timing=True); e.record(); events.append(e)
         mark()
-        fe._check(L.fastecc_b200_rs_encode_shard_pass_p2p(X, self._yp, self.N, self.G, self.rank, self.S, self.S, 0, st))
+        fe._check(L.fastecc_b200_rs_encode_shard_pass_p2p(X, yp, self.N, self.G, self.rank, width, self.S, 0, st))
         mark()
         self._barrier()
         mark()
-        fe._check(L.fastecc_b200_rs_encode_shard_pass_p2p(Y, self._xp, self.N, self.G, self.rank, self.S, self.S, 1, st))
+        fe._check(L.fastecc_b200_rs_encode_shard_pass_p2p(Y, xp, self.N, self.G, self.rank, width, self.S, 1, st))
         mark()
         self._barrier()
         mark()
-        fe._check(L.fastecc_b200_rs_encode_shard_pass_p2p(X, self._xp, self.N, self.G, self.rank, self.S, self.S, 2, st))
+        fe._check(L.fastecc_b200_rs_encode_shard_pass_p2p(X, xp, self.N, self.G, self.rank, width, self.S, 2, st))
         mark()
+
+    def encode(self, events=None):
+        """events: optional list that receives 6 CUDA events bracketing pass A, barrier, pass BC, barrier, pass D."""
+        self._passes(0, self.S, events)
         return self.x
+
+    def encode_host(self, h_in, h_out=None, chunk_words: int = 256):
+        """End to end from host memory: h_in is this rank's [N/G, S] uint32 numpy array (global block l*G + rank = row l),
+        ideally pinned (fastecc_b200_host_alloc); the parity rows are written to h_out (default: in place).  The word
+        columns are independent codewords, so the array moves in column chunks: H2D of chunk c+1, the three sharded passes
+        of chunk c and D2H of chunk c-1 overlap on three streams.  Collective, blocking."""
+        import torch
+        import fastecc_b200 as fe
+        rows, S = self.N // self.G, self.S
+        h_out = h_in if h_out is None else h_out
+        for h in (h_in, h_out):
+            if h.dtype.itemsize != 4 or h.shape != (rows, S) or not h.flags.c_contiguous:
+                raise ValueError("host shard must be a C-contiguous [N/G, S] array of 32-bit words")
+        if chunk_words % 4 or chunk_words <= 0:
+            raise ValueError("chunk_words must be a positive multiple of 4")
+        if self._s_h2d is None:
+            self._s_h2d, self._s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
+        cur = torch.cuda.current_stream()
+        L = self._lib
+        src, dst, X = h_in.ctypes.data, h_out.ctypes.data, self._own[0]
+        self._s_h2d.wait_stream(cur)                                    # earlier work on the buffers is done before we overwrite them
+        for c0 in range(0, S, chunk_words):
+            w = min(chunk_words, S - c0)
+            fe._check(L.fastecc_b200_copy2d_async(X + 4 * c0, 4 * S, src + 4 * c0, 4 * S, 4 * w, rows, 1, self._s_h2d.cuda_stream))
+            ev = torch.cuda.Event(); ev.record(self._s_h2d); cur.wait_event(ev)
+            self._passes(c0, w)
+            ev = torch.cuda.Event(); ev.record(cur); self._s_d2h.wait_event(ev)
+            fe._check(L.fastecc_b200_copy2d_async(dst + 4 * c0, 4 * S, X + 4 * c0, 4 * S, 4 * w, rows, 0, self._s_d2h.cuda_stream))
+        self._s_d2h.synchronize()
+        cur.synchronize()
+        return h_out
 
     def close(self):
         import torch
