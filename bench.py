@@ -616,7 +616,7 @@ def run_sharded(args, fe, rank, world, local, dev, numa):
                                        "(peer-mapped, CUDA IPC), 2 one-word all-reduce barriers" % world
                                        if fused else "ONE transform over %d GPUs: cyclic blocks, 3 local passes + 2 NCCL all-to-all" % world),
                        "l2": "local arrays (%.0f MiB per GPU) exceed L2" % (N * S * 4 / world / 2**20)},
-            "roofline": {"bound": "nvlink", "kernel": "ntt_pass_dual_kernel<9,1> (A) + ntt_pass_kernel<10,2,2> (BC): sharded-store instantiations",
+            "roofline": {"bound": "nvlink", "kernel": "ntt_pass_kernel<9,1,2> (A) + ntt_pass_kernel<10,2,2> (BC): the instantiations whose stores pick a destination GPU",
                          "achieved": a2a_bytes / step_s / 1e9, "peak": link, "unit": "GB/s",
                          "frac": t_link / step_s, "traffic": None,
                          "note": "bytes each GPU sends to its peers per encode (2 exchanges of (G-1)/G of the local array) / step time, against the measured 770 GB/s per-direction peer bandwidth"},

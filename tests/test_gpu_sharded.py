@@ -48,6 +48,45 @@ def _worker_p2p(rank, world, port, L, S, q):
     dist.destroy_process_group()
 
 
+def _worker_p2p_headline(rank, world, port, L, S, q):
+    """BASELINE config 4 at full size: fill A (data0[i] = i % P, RS.cpp:28-29) dealt cyclically, one sharded encode, the
+    gathered parity must hash (main.cpp:203-212) to the golden value of the unmodified reference; the same through
+    encode_host (column-chunked H2D / passes / D2H pipeline) from a host shard."""
+    import json
+    import torch
+    import torch.distributed as dist
+    import fastecc_b200 as fe
+    from fastecc_b200 import sharded
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    fe.init(rank)
+    N = 1 << L
+    golden = json.load(open(os.path.join(ROOT, "tests", "golden", "survey_8c.json")))
+    want = [g[3] for g in golden["encode_fillA"] if g[0] == L and g[1] == S][0]
+    rows = N // world
+    idx = (np.arange(rows, dtype=np.uint64)[:, None] * np.uint64(world) + np.uint64(rank)) * np.uint64(S) + np.arange(S, dtype=np.uint64)[None, :]
+    shard = (idx % np.uint64(0xFFF00001)).astype(np.uint32)
+    del idx
+    enc = sharded.P2PShardedEncoder(N, S)
+    enc.x.copy_(torch.from_numpy(shard.view(np.int32)))
+    out = enc.encode().clone()
+    host = shard.copy()
+    enc.encode_host(host)                                                  # pageable host memory is allowed, pinned is faster
+    same = bool(np.array_equal(host, out.cpu().numpy().view(np.uint32)))
+    gathered = [torch.empty_like(out) for _ in range(world)] if rank == 0 else None
+    dist.gather(out, gathered, dst=0)
+    flags = torch.tensor([1 if same else 0], device="cuda")
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        par = np.empty((N, S), dtype=np.uint32)
+        for r in range(world):
+            par[r::world] = gathered[r].cpu().numpy().view(np.uint32)
+        q.put(bool(fe.reference_hash(par) == want and int(flags.item()) == 1 and int(par.max()) < 0xFFF00001))
+    enc.close()
+    dist.destroy_process_group()
+
+
 def _worker(rank, world, port, L, S, q):
     import torch
     import torch.distributed as dist
@@ -96,6 +135,11 @@ def _run(worker, L, S):
 @pytest.mark.parametrize("L,S", [(16, 64), (17, 1024)])
 def test_p2p_fused_exchange_encode_on_gpus(L, S):
     _run(_worker_p2p, L, S)
+
+
+def test_p2p_fused_exchange_headline_hash_all_gpus():
+    """N = 2^19 x 4096 B over every visible GPU (2, 4 or 8): golden parity hash 4272226309."""
+    _run(_worker_p2p_headline, 19, 1024)
 
 
 @pytest.mark.parametrize("L,S", [(11, 64), (16, 1024)])
