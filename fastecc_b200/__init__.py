@@ -60,6 +60,7 @@ def lib() -> ctypes.CDLL:
         L.fastecc_b200_row_scale_dev.argtypes = [vp, sz, sz, sz, vp, vp]; L.fastecc_b200_row_scale_dev.restype = ci
         L.fastecc_b200_rs_encode_shard_pass.argtypes = [vp, sz, ci, ci, sz, sz, ci, vp]; L.fastecc_b200_rs_encode_shard_pass.restype = ci
         L.fastecc_b200_rs_encode_shard_pass_p2p.argtypes = [vp, vp, sz, ci, ci, sz, sz, ci, vp]; L.fastecc_b200_rs_encode_shard_pass_p2p.restype = ci
+        L.fastecc_b200_ntt_shard_pass_p2p.argtypes = [vp, vp, sz, ci, ci, sz, sz, ci, ci, vp]; L.fastecc_b200_ntt_shard_pass_p2p.restype = ci
         L.fastecc_b200_dev_alloc.argtypes = [sz]; L.fastecc_b200_dev_alloc.restype = vp
         L.fastecc_b200_dev_free.argtypes = [vp]; L.fastecc_b200_dev_free.restype = None
         L.fastecc_b200_ipc_export.argtypes = [vp, vp]; L.fastecc_b200_ipc_export.restype = ci
@@ -69,6 +70,7 @@ def lib() -> ctypes.CDLL:
         L.fastecc_b200_rs_encode_dev_timed.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp]; L.fastecc_b200_rs_encode_dev_timed.restype = ci
         L.fastecc_b200_shard_geometry.argtypes = [sz, ci, vp, vp, vp]; L.fastecc_b200_shard_geometry.restype = ci
         L.fastecc_b200_copy2d_async.argtypes = [vp, sz, vp, sz, sz, sz, ci, vp]; L.fastecc_b200_copy2d_async.restype = ci
+        L.fastecc_b200_pin_host_buffers.argtypes = [ci]; L.fastecc_b200_pin_host_buffers.restype = ci
         L.fastecc_b200_hash_u32.argtypes = [vp, sz, sz]; L.fastecc_b200_hash_u32.restype = ctypes.c_uint32
         L.fastecc_b200_host_alloc.argtypes = [sz]; L.fastecc_b200_host_alloc.restype = vp
         L.fastecc_b200_host_free.argtypes = [vp]; L.fastecc_b200_host_free.restype = None
@@ -87,6 +89,11 @@ def init(device: int = 0) -> None:
 
 def shutdown() -> None:
     lib().fastecc_b200_shutdown()
+
+
+def pin_host_buffers(enable: bool = True) -> None:
+    """Opt in to page-locking large pageable arrays passed to MFA_NTT / EncodeReedSolomon_body in place (see the header)."""
+    _check(lib().fastecc_b200_pin_host_buffers(1 if enable else 0))
 
 
 def kernel_launches() -> int:

@@ -65,6 +65,8 @@ struct Context {
     SharedBuf packed;    // repacked copy for unaligned device layouts
     DevBuf staging;      // device copy for the host (T**) entry points (serialised by g_mu)
     std::map<uint32_t, TableSet> tables;              // per (mode, log2 N, ...)
+    bool pin_caller = false;                          // fastecc_b200_pin_host_buffers()
+    std::vector<std::pair<char*, size_t>> registered; // caller buffers we page-locked in place (cudaHostRegister)
     cudaStream_t stream = nullptr;       // compute
     cudaStream_t h2d = nullptr, d2h = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_done;
@@ -91,6 +93,26 @@ int check_shape(size_t N, size_t size, size_t max_log, const char* who)
         return fail(FASTECC_B200_EINVAL, "%s: N=%zu must be a power of two in [1, 2^%zu] (P-1 = 2^20*4095)", who, N, max_log);
     if (size > 0xFFFFFFF0u) return fail(FASTECC_B200_EINVAL, "%s: SIZE too large", who);
     return 0;
+}
+
+// Host (T**) entry points on a large contiguous PAGEABLE array: cudaMemcpy2DAsync would be staged through the driver's bounce
+// buffers, synchronously, and nothing would overlap.  When the caller has opted in (fastecc_b200_pin_host_buffers: it keeps
+// the array alive and calls again on it, like the reference's drivers, RS.cpp:31 / main.cpp:244), the array is page-locked in
+// place once -- about 0.2 s per GiB -- and every later call runs the pinned, pipelined path.  Failure is not an error.
+void pin_caller_array(Context* c, void* base, size_t bytes)
+{
+    if (!c->pin_caller || bytes < ((size_t)32 << 20)) return;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, base) != cudaSuccess) { cudaGetLastError(); return; }
+    if (at.type != cudaMemoryTypeUnregistered) return;                      // already pinned (by us earlier, or by the caller)
+    char* b = (char*)base;
+    for (size_t i = 0; i < c->registered.size();) {                         // a stale, overlapping registration (the caller re-allocated): drop it
+        auto& r = c->registered[i];
+        if (b < r.first + r.second && r.first < b + bytes) { cudaHostUnregister(r.first); cudaGetLastError(); r = c->registered.back(); c->registered.pop_back(); }
+        else ++i;
+    }
+    if (cudaHostRegister(base, bytes, cudaHostRegisterDefault) == cudaSuccess) c->registered.emplace_back(b, bytes);
+    else cudaGetLastError();
 }
 
 // Stage tables of `plan` under cache key `key`: built on first use (into a local set that enters the cache only when every
@@ -233,6 +255,7 @@ int run_host(uint32_t** data, size_t N, size_t size, int mode, const char* who)
     size_t cw = chunk_env ? (chunk_env + 15) / 16 * 16 : 128;
     const bool pipelined = contiguous && pitch == size && size >= 2 * cw && N * size * 4 >= ((size_t)32 << 20);
     if (pipelined) {
+        pin_caller_array(c, data[0], N * size * sizeof(uint32_t));
         const size_t nchunks = (size + cw - 1) / cw;
         while (c->ev_in.size() < nchunks) { cudaEvent_t e; CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->ev_in.push_back(e); }
         while (c->ev_done.size() < nchunks) { cudaEvent_t e; CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->ev_done.push_back(e); }
@@ -301,6 +324,7 @@ void fastecc_b200_shutdown(void)
     cudaSetDevice(g_ctx->device);
     cudaDeviceSynchronize();
     g_ctx->scratch.destroy(); g_ctx->packed.destroy(); g_ctx->staging.release();
+    for (auto& r : g_ctx->registered) cudaHostUnregister(r.first);
     for (auto& kv : g_ctx->tables) for (auto& sl : kv.second.slots) { sl.buf.release(); if (sl.ready) cudaEventDestroy(sl.ready); }
     if (g_ctx->d_tw) cudaFree(g_ctx->d_tw);
     if (g_ctx->stream) cudaStreamDestroy(g_ctx->stream);
@@ -345,8 +369,8 @@ int fastecc_b200_shard_geometry(size_t N, int n_ranks, size_t* N1, size_t* N2, i
     const uint32_t LN = ilog2(N), L1 = LN <= (uint32_t)kMaxLogR ? LN : split_l1(LN);
     if (N1) *N1 = (size_t)1 << L1;
     if (N2) *N2 = (size_t)1 << (LN - L1);
-    if (fused_exchange_ok) *fused_exchange_ok = n_ranks >= 2 && shard_p2p_supported(N, (uint32_t)n_ranks) ? 1 : 0;
-    return n_ranks < 2 || shard_supported(N, (uint32_t)n_ranks) ? 0 : fail(FASTECC_B200_EINVAL, "fastecc_b200_shard_geometry: N=%zu cannot be sharded over %d ranks", N, n_ranks);
+    if (fused_exchange_ok) *fused_exchange_ok = n_ranks >= 2 ? (shard_p2p_supported(N, (uint32_t)n_ranks) ? 1 : 0) | (ntt_shard_p2p_supported(N, (uint32_t)n_ranks) ? 2 : 0) : 0;
+    return n_ranks < 2 || shard_supported(N, (uint32_t)n_ranks) || ntt_shard_p2p_supported(N, (uint32_t)n_ranks) ? 0 : fail(FASTECC_B200_EINVAL, "fastecc_b200_shard_geometry: N=%zu cannot be sharded over %d ranks", N, n_ranks);
 }
 
 int fastecc_b200_copy2d_async(void* dst, size_t dst_pitch_bytes, const void* src, size_t src_pitch_bytes, size_t width_bytes, size_t rows, int to_device, void* stream)
@@ -481,6 +505,26 @@ int fastecc_b200_rs_encode_shard_pass_p2p(const uint32_t* d_src, uint32_t* const
     return 0;
 }
 
+int fastecc_b200_ntt_shard_pass_p2p(const uint32_t* d_src, uint32_t* const* d_peers, size_t N, int n_ranks, int rank, size_t size, size_t pitch,
+                                    int inverse, int which, void* stream)
+{
+    const char* who = "fastecc_b200_ntt_shard_pass_p2p";
+    Context* c = g_ctx;
+    if (!c) return fail(FASTECC_B200_ENOINIT, "%s: call fastecc_b200_init() first", who);
+    if (!d_src || !d_peers || which < 0 || which > 1 || rank < 0 || rank >= n_ranks) return fail(FASTECC_B200_EINVAL, "%s: bad arguments", who);
+    if (!ntt_shard_p2p_supported(N, (uint32_t)n_ranks))
+        return fail(FASTECC_B200_EINVAL, "%s: N=%zu cannot be sharded over %d ranks (need 2^11..2^20, ranks <= 8, first tile height >= 32 * ranks)", who, N, n_ranks);
+    if (size == 0 || pitch < size || pitch > 0xFFFFFFF0u || pitch % 4 || ((uintptr_t)d_src) % 16) return fail(FASTECC_B200_EINVAL, "%s: needs SIZE >= 1, 16-byte aligned buffers and pitch %% 4 == 0", who);
+    for (int r = 0; r < n_ranks; ++r)
+        if (!d_peers[r] || ((uintptr_t)d_peers[r]) % 16) return fail(FASTECC_B200_EINVAL, "%s: peer buffer %d missing or misaligned", who, r);
+    if ((unsigned long long)(N / n_ranks) * (pitch / 4) >= (1ull << 32)) return fail(FASTECC_B200_EINVAL, "%s: local buffer too large", who);
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<PassParams> one{plan_ntt_shard_p2p(d_src, d_peers, c->d_tw, (uint32_t)pitch, (uint32_t)size, N, (uint32_t)n_ranks, (uint32_t)rank, inverse != 0, which)};
+    if (int rc = attach_tables(c, 0xC0000000u | (inverse ? 1u : 0u) << 28 | (uint32_t)n_ranks << 16 | (uint32_t)rank << 8 | ilog2(N), one, st, which, 2)) return rc;
+    CUDA_TRY(launch_pass(one[0], c->num_sms, st)); g_launches++;
+    return 0;
+}
+
 // Device buffers that can be mapped into the other ranks' address spaces (cudaMalloc + CUDA IPC: torch's caching
 // allocator hands out sub-blocks, which cannot be exported).
 void* fastecc_b200_dev_alloc(size_t bytes)
@@ -518,6 +562,19 @@ int fastecc_b200_ntt_u32(uint32_t** data, size_t N, size_t size, int inverse)
 
 int fastecc_b200_rs_encode(uint32_t** data, size_t N, size_t size)
 { return run_host(data, N, size, 2, "fastecc_b200_rs_encode"); }
+
+int fastecc_b200_pin_host_buffers(int enable)
+{
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    if (!g_ctx) return fail(FASTECC_B200_ENOINIT, "fastecc_b200_pin_host_buffers: call fastecc_b200_init() first");
+    g_ctx->pin_caller = enable != 0;
+    if (!enable) {                                                          // turning it off also releases what was page-locked so far
+        CUDA_TRY(cudaDeviceSynchronize());
+        for (auto& r : g_ctx->registered) { cudaHostUnregister(r.first); cudaGetLastError(); }
+        g_ctx->registered.clear();
+    }
+    return 0;
+}
 
 uint32_t fastecc_b200_hash_u32(uint32_t* const* data, size_t N, size_t size)
 {

@@ -253,6 +253,47 @@ inline PassParams plan_encode_shard_p2p(const uint32_t* src, uint32_t* const* pe
     return p;
 }
 
+// ONE standalone transform (MFA_NTT, ntt.cpp:382-447) sharded the same way (BASELINE config 5 "at 1 and 8 GPUs"): blocks dealt
+// cyclically for the input AND the output.  Pass A' (for each local n2, DIT over n1) reads the local X and stores element k1
+// into row n2*(N1/G) + k1/G of the Y of rank k1 mod G -- the transpose between the two steps of the four-step algorithm
+// (TransposeMatrix, ntt.cpp:322-341) as peer stores; pass B' (for each local k1, DIT over n2 with the four-step twiddle as input
+// twist) is then local, Y -> X, and its output element k2 = global block k1 + N1*k2 is again owned by this rank (N1 % G == 0).
+inline bool ntt_shard_p2p_supported(size_t N, uint32_t G)
+{
+    if (!is_pow2(N) || !is_pow2(G) || G < 2 || G > kMaxPeers) return false;
+    const uint32_t LN = ilog2(N);
+    if (LN <= (uint32_t)kMaxLogR || LN > 20) return false;
+    const uint32_t L1 = split_l1(LN), L2 = LN - L1, lg = ilog2(G);
+    return L1 >= 5 + lg && L2 >= lg;
+}
+inline PassParams plan_ntt_shard_p2p(const uint32_t* src, uint32_t* const* peers, const uint4* tw, uint32_t pitch_words, uint32_t size_words,
+                                     size_t N, uint32_t G, uint32_t rank, bool inverse, int which)
+{
+    Buffers b{const_cast<uint32_t*>(src), nullptr, tw, pitch_words, size_words};
+    const uint32_t LN = ilog2(N), L1 = split_l1(LN), L2 = LN - L1;
+    const uint32_t N1 = 1u << L1, N2 = 1u << L2;
+    const long long p = (long long)(kM / N) * (inverse ? -1 : 1);       // w = g^p
+    PassParams a;
+    if (which == 0) {
+        a = base_pass(b, L1);
+        a.nsets = N2 / G;
+        a.src_set_stride = 1; a.src_row_stride = N2 / G;
+        a.xf[0] = Xform{emod(p * (long long)N2), 0, 0};
+        a.log_g = ilog2(G);
+        for (uint32_t r = 0; r < kMaxPeers; ++r) a.peers[r] = peers[r < G ? r : 0];
+        a.dst_row_stride = 1; a.dst_set_stride = N1; a.dst_row_offset = rank * (N1 / G);
+    } else {
+        a = base_pass(b, L2);
+        a.nsets = N1 / G;
+        a.src_set_stride = 1; a.src_row_stride = N1 / G;
+        a.dst_set_stride = 1; a.dst_row_stride = N1 / G;
+        a.xf[0] = Xform{emod(p * (long long)N1), emod(p * (long long)rank), emod(p * (long long)G)};
+        a.canonical_out = 1;
+    }
+    a.src = src; a.dst = peers[rank];
+    return a;
+}
+
 // Per-set stage tables of a pass: [set][xfi][R] entries of 16 bytes; a single shared set when no twist depends on it.
 inline uint32_t table_sets(const PassParams& P)
 {

@@ -29,7 +29,7 @@ def _geometry(N: int, G: int):
     n1, n2, ok = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_int()
     if fe.lib().fastecc_b200_shard_geometry(N, G, ctypes.byref(n1), ctypes.byref(n2), ctypes.byref(ok)) != 0:
         raise ValueError("N2 = %d must be a multiple of the number of ranks" % n2.value)
-    return n1.value, n2.value, bool(ok.value)
+    return n1.value, n2.value, bool(ok.value & 1)
 
 
 def geometry(N: int, G: int):
@@ -89,12 +89,25 @@ def gpu_pass_runner(N: int, G: int, rank: int):
     return run
 
 
+def _support_bits(N: int, G: int) -> int:
+    """bit 0: the fused-exchange ENCODE passes, bit 1: the fused-exchange NTT passes support (N, G)  (csrc/plan.h)."""
+    import ctypes
+    import fastecc_b200 as fe
+    ok = ctypes.c_int()
+    if N < 2 or N & (N - 1) or G < 2 or G & (G - 1):
+        return 0
+    fe.lib().fastecc_b200_shard_geometry(N, G, None, None, ctypes.byref(ok))
+    return ok.value
+
+
 def p2p_supported(N: int, G: int) -> bool:
     """csrc/plan.h shard_p2p_supported(): <= 8 ranks and every thread's 32 output rows on one rank for both tile heights."""
-    try:
-        return _geometry(N, G)[2]
-    except ValueError:
-        return False
+    return bool(_support_bits(N, G) & 1)
+
+
+def p2p_ntt_supported(N: int, G: int) -> bool:
+    """csrc/plan.h ntt_shard_p2p_supported(): N = 2^11..2^20, <= 8 ranks, first tile height >= 32 * ranks."""
+    return bool(_support_bits(N, G) & 2)
 
 
 class _RawCudaBuffer:
@@ -117,8 +130,9 @@ class P2PShardedEncoder:
         import fastecc_b200 as fe
         self.N, self.S, self.group = N, S, group
         self.G, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        if not p2p_supported(N, self.G) or S % 4:
-            raise ValueError("fused-exchange sharding needs N = 2^15..2^19 (fewer ranks: from 2^12), <= 8 ranks, SIZE % 4 == 0")
+        self._can_encode, self._can_ntt = p2p_supported(N, self.G), p2p_ntt_supported(N, self.G)
+        if not (self._can_encode or self._can_ntt) or S % 4:
+            raise ValueError("fused-exchange sharding needs <= 8 ranks, SIZE % 4 == 0 and N = 2^15..2^19 (encode; fewer ranks: from 2^12) or up to 2^20 (NTT)")
         self._lib = L = fe.lib()
         self._dev = torch.cuda.current_device()
         fe.init(self._dev)
@@ -190,7 +204,32 @@ class P2PShardedEncoder:
 
     def encode(self, events=None):
         """events: optional list that receives 6 CUDA events bracketing pass A, barrier, pass BC, barrier, pass D."""
+        if not self._can_encode:
+            raise ValueError("N = %d cannot be encoded over %d ranks with the fused exchange" % (self.N, self.G))
         self._passes(0, self.S, events)
+        return self.x
+
+    def ntt(self, inverse: bool = False, events=None):
+        """ONE standalone transform of the N blocks (MFA_NTT, ntt.cpp:382-447; unnormalised inverse), in place in enc.x, cyclic
+        blocks in and out: pass A' stores into the owners' Y over NVLink, one barrier, pass B' is local.  events: 4 CUDA events."""
+        import torch
+        import fastecc_b200 as fe
+        if not self._can_ntt:
+            raise ValueError("N = %d cannot be transformed over %d ranks with the fused exchange" % (self.N, self.G))
+        L, st = self._lib, torch.cuda.current_stream().cuda_stream
+        X, Y = self._own
+        xp, yp = self._peer_arrays(0)
+
+        def mark():
+            if events is not None:
+                e = torch.cuda.Event(enable_timing=True); e.record(); events.append(e)
+        mark()
+        fe._check(L.fastecc_b200_ntt_shard_pass_p2p(X, yp, self.N, self.G, self.rank, self.S, self.S, 1 if inverse else 0, 0, st))
+        mark()
+        self._barrier()
+        mark()
+        fe._check(L.fastecc_b200_ntt_shard_pass_p2p(Y, xp, self.N, self.G, self.rank, self.S, self.S, 1 if inverse else 0, 1, st))
+        mark()
         return self.x
 
     def encode_host(self, h_in, h_out=None, chunk_words: int = 256):

@@ -39,6 +39,9 @@ inline void MFA_NTT<uint32_t,0xFFF00001> (uint32_t** data, size_t N, size_t SIZE
             fprintf(stderr, "fastecc_b200: %s\n", fastecc_b200_last_error());
             abort();
         }
+        // the drivers allocate their block array once and never free it (RS.cpp:31, main.cpp:244): let the library page-lock it
+        // in place on first sight (FASTECC_B200_NO_PIN=1: leave it pageable, for comparison)
+        fastecc_b200_pin_host_buffers(getenv("FASTECC_B200_NO_PIN") ? 0 : 1);
         ready = true;
     }
     if (fastecc_b200_ntt_u32(data, N, SIZE, InvNTT ? 1 : 0) != 0) {

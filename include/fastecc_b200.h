@@ -53,6 +53,14 @@ int  fastecc_b200_num_sms(void);
  * through data[i]).  The inverse transform is unnormalised, as in the reference.  1 <= N <= 2^20, power of two. */
 int fastecc_b200_ntt_u32(uint32_t** data, size_t N, size_t SIZE_words, int inverse);
 
+/* Opt-in for callers that keep one large block array alive and transform it repeatedly from PAGEABLE memory, the way the
+ * reference's drivers do (RS.cpp:31-33, main.cpp:244-247: allocated once, never freed): the host entry points then page-lock
+ * such an array in place on first sight (cudaHostRegister, about 0.2 s per GiB, once) so that its transfers pipeline like
+ * pinned memory; registrations are dropped by fastecc_b200_pin_host_buffers(0) and at fastecc_b200_shutdown().  While it is enabled, arrays
+ * that were passed to the host entry points must not be freed (a page-locked range that is unmapped and re-allocated would
+ * be transferred from its old pages).  Off by default; fastecc_b200/shim/ntt.cpp turns it on. */
+int fastecc_b200_pin_host_buffers(int enable);
+
 /* Replaces the timed body of  template<T,P> void EncodeReedSolomon(size_t N, size_t SIZE)   RS.cpp:41-63
  * (iNTT, multiply block i by root_2N^i / N, NTT): N data blocks in, N parity blocks out, same buffers.
  * 1 <= N <= 2^19 (N = 2^20 is rejected: the reference silently computes garbage there, GF(p).cpp:274). */
@@ -119,8 +127,15 @@ int fastecc_b200_rs_encode_shard_pass(uint32_t* d_local, size_t N, int n_ranks, 
  * both factors of N = N1*N2 (csrc/plan.h split_l1) at least 32*n_ranks, so that the 32 rows a thread stores go to one rank. */
 int fastecc_b200_rs_encode_shard_pass_p2p(const uint32_t* d_src, uint32_t* const* d_peers, size_t N, int n_ranks, int rank,
                                           size_t SIZE_words, size_t pitch_words, int which, void* stream);
+/* ONE standalone transform (MFA_NTT, ntt.cpp:382-447; unnormalised inverse) sharded the same way: cyclic blocks in and out.
+ *   which 0: reads the local X, stores into the Ys of the owners (the four-step transpose as peer stores)   d_src = X_local, d_peers[r] = rank r's Y
+ *   which 1: local, Y -> X                                                                                  d_src = Y_local, d_peers[rank] = X_local
+ * with one cross-rank barrier between them.  N = 2^11 .. 2^20, n_ranks = 2, 4 or 8, first tile height (N1 of csrc/plan.h) >= 32 * n_ranks. */
+int fastecc_b200_ntt_shard_pass_p2p(const uint32_t* d_src, uint32_t* const* d_peers, size_t N, int n_ranks, int rank,
+                                    size_t SIZE_words, size_t pitch_words, int inverse, int which, void* stream);
+
 /* The decomposition N = N1 * N2 the passes use (csrc/plan.h split_l1, FASTECC_B200_SPLIT honoured), for callers that do the
- * exchange themselves; *fused_exchange_ok = 1 when the _p2p passes support (N, n_ranks).  Fails if N cannot be sharded. */
+ * exchange themselves; *fused_exchange_ok: bit 0 = the encode _p2p passes, bit 1 = the NTT _p2p passes support (N, n_ranks).  Fails if N cannot be sharded. */
 int fastecc_b200_shard_geometry(size_t N, int n_ranks, size_t* N1, size_t* N2, int* fused_exchange_ok);
 /* cudaMemcpy2DAsync between pinned host memory and a device buffer (column chunks of a block array), for pipelined
  * host <-> device staging around the sharded passes (fastecc_b200/sharded.py encode_host). */

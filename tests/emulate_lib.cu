@@ -24,6 +24,13 @@ extern "C" int emu_rs_encode_shard_pass_p2p(const uint32_t* src, uint32_t* const
                                        N, (uint32_t)n_ranks, (uint32_t)rank, which));
     return 0;
 }
+extern "C" int emu_ntt_shard_pass_p2p(const uint32_t* src, uint32_t* const* peers, size_t N, int n_ranks, int rank, size_t size, size_t pitch, int inverse, int which)
+{
+    if (!ntt_shard_p2p_supported(N, (uint32_t)n_ranks) || pitch % 4 || which < 0 || which > 1) return -1;
+    emulate_pass(plan_ntt_shard_p2p(src, peers, reinterpret_cast<const uint4*>(power_table().data()), (uint32_t)pitch, (uint32_t)size,
+                                    N, (uint32_t)n_ranks, (uint32_t)rank, inverse != 0, which));
+    return 0;
+}
 extern "C" int emu_rs_encode_asym(uint32_t* x, uint32_t* y, size_t N, size_t M, size_t size, size_t pitch)
 {
     if (!asym_native(N, M)) return -1;

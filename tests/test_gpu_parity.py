@@ -78,6 +78,33 @@ def test_host_pointer_table_api(fecc, oracle, L, S):
     b = a.copy(); fecc.EncodeReedSolomon_body(b, N, S); assert np.array_equal(b, ol.o_encode(oracle, a))
 
 
+@pytest.mark.parametrize("pin", [False, True])
+def test_host_api_at_pipelined_sizes(fecc, oracle, pin):
+    """The host T** path above its pipelining threshold (32 MiB: column chunks on three streams, csrc/api.cu run_host) --
+    what bench.py's e2e times -- from pageable memory, with and without in-place page-locking of the caller's array:
+    2^16 x 4 KiB against the oracle word for word, then the headline 2^19 x 4 KiB against the reference's golden hashes."""
+    fecc.pin_host_buffers(pin)
+    keep = []                                  # the contract of pin_host_buffers: arrays stay alive while it is enabled
+    try:
+        N, S = 1 << 16, 1024
+        a = ol.fill_B(oracle, N, S)
+        b = a.copy(); keep.append(b); fecc.EncodeReedSolomon_body(b, N, S); assert np.array_equal(b, ol.o_encode(oracle, a))
+        b = a.copy(); keep.append(b); fecc.MFA_NTT(b, N, S, False); assert np.array_equal(b, ol.o_ntt(oracle, a, False))
+        b = a.copy(); keep.append(b); fecc.MFA_NTT(b, N, S, True); assert np.array_equal(b, ol.o_ntt(oracle, a, True))
+        N = 1 << 19
+        _, _, h0, h1 = [g for g in G["encode_fillA"] if g[0] == 19][0]
+        a = ol.fill_A(oracle, N, S); keep.append(a)
+        assert fecc.reference_hash(a) == h0
+        fecc.EncodeReedSolomon_body(a, N, S)
+        assert fecc.reference_hash(a) == h1
+        oracle.oracle_fill_A(a.ctypes.data, N * S)                       # same array again: the second call finds it page-locked
+        fecc.MFA_NTT(a, N, S, False)
+        assert fecc.reference_hash(a) == G["ntt_fillA_4096B"]["19"][1]
+    finally:
+        fecc.pin_host_buffers(False)               # also releases every registration
+        del keep
+
+
 def test_host_scattered_blocks(fecc, oracle):
     """Blocks at arbitrary addresses, in permuted order (the reference leaves its own table permuted)."""
     N, S = 64, 12

@@ -87,6 +87,62 @@ def _worker_p2p_headline(rank, world, port, L, S, q):
     dist.destroy_process_group()
 
 
+def _worker_p2p_ntt(rank, world, port, L, S, q):
+    """Sharded standalone transform: small orders against the oracle word for word; L >= 19 against the reference's golden
+    "ntt n L 4096" hashes (fill A), plus inverse(forward(x)) == N * x."""
+    import json
+    import torch
+    import torch.distributed as dist
+    import oracle_lib as ol
+    import fastecc_b200 as fe
+    from fastecc_b200 import sharded
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    fe.init(rank)
+    N, P = 1 << L, 0xFFF00001
+    rows = N // world
+    enc = sharded.P2PShardedEncoder(N, S)
+    ok = True
+    if L < 19:
+        o = ol.load_oracle()
+        full = ol.fill_B(o, N, S)
+        for inverse in (False, True):
+            enc.x.copy_(torch.from_numpy(np.ascontiguousarray(full[rank::world]).view(np.int32)))
+            out = enc.ntt(inverse).clone()
+            gathered = [torch.empty_like(out) for _ in range(world)] if rank == 0 else None
+            dist.gather(out, gathered, dst=0)
+            if rank == 0:
+                res = np.empty((N, S), dtype=np.uint32)
+                for r in range(world):
+                    res[r::world] = gathered[r].cpu().numpy().view(np.uint32)
+                ok = ok and bool(np.array_equal(res, ol.o_ntt(o, full, inverse)))
+    else:
+        golden = json.load(open(os.path.join(ROOT, "tests", "golden", "survey_8c.json")))["ntt_fillA_4096B"][str(L)]
+        idx = (np.arange(rows, dtype=np.uint64)[:, None] * np.uint64(world) + np.uint64(rank)) * np.uint64(S) + np.arange(S, dtype=np.uint64)[None, :]
+        shard = torch.from_numpy((idx % np.uint64(P)).astype(np.uint32).view(np.int32)).cuda()
+        del idx
+        enc.x.copy_(shard)
+        out = enc.ntt(False).clone()
+        enc.ntt(True)
+        want = (shard.long() & 0xFFFFFFFF) * N % P                         # unnormalised inverse: N * x
+        same = bool(((enc.x.long() & 0xFFFFFFFF) == want).all())
+        del want
+        gathered = [torch.empty_like(out) for _ in range(world)] if rank == 0 else None
+        dist.gather(out, gathered, dst=0)
+        flags = torch.tensor([1 if same else 0], device="cuda")
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            res = np.empty((N, S), dtype=np.uint32)
+            for r in range(world):
+                res[r::world] = gathered[r].cpu().numpy().view(np.uint32)
+            ok = bool(fe.reference_hash(res) == golden[1] and int(flags.item()) == 1)
+    enc.close()
+    if rank == 0:
+        q.put(ok)
+    dist.destroy_process_group()
+
+
 def _worker(rank, world, port, L, S, q):
     import torch
     import torch.distributed as dist
@@ -135,6 +191,17 @@ def _run(worker, L, S):
 @pytest.mark.parametrize("L,S", [(16, 64), (17, 1024)])
 def test_p2p_fused_exchange_encode_on_gpus(L, S):
     _run(_worker_p2p, L, S)
+
+
+@pytest.mark.parametrize("L,S", [(12, 64), (16, 256), (19, 1024), (20, 1024)])
+def test_p2p_sharded_ntt_on_gpus(L, S):
+    """BASELINE config 5 end points (2^19, 2^20 x 4096 B: golden hashes of `ntt n L 4096`) and two small orders vs the oracle."""
+    import torch
+    from fastecc_b200 import sharded
+    world = min(torch.cuda.device_count(), 8)
+    if world >= 2 and not sharded.p2p_ntt_supported(1 << L, 1 << (world.bit_length() - 1)):
+        pytest.skip("this order cannot split its first-pass tiles over that many ranks")
+    _run(_worker_p2p_ntt, L, S)
 
 
 def test_p2p_fused_exchange_headline_hash_all_gpus():

@@ -46,6 +46,31 @@ def test_p2p_sharded_passes_match_oracle(G, L, S):
     assert np.array_equal(par, ol.o_encode(o, full))
 
 
+@pytest.mark.parametrize("G,L,S,inverse", [(2, 11, 8, 0), (2, 15, 12, 1), (4, 14, 4, 0), (8, 16, 4, 1), (8, 19, 4, 0), (8, 20, 4, 0), (4, 20, 4, 1)])
+def test_p2p_sharded_ntt_passes_match_oracle(G, L, S, inverse):
+    """Standalone transform (plan_ntt_shard_p2p): pass A' scatters into the owners' Y, pass B' is local; output cyclic again."""
+    _build_emulator()
+    emu = ctypes.CDLL(EMU)
+    f = emu.emu_ntt_shard_pass_p2p
+    f.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, ctypes.c_int]
+    N = 1 << L
+    o = ol.load_oracle()
+    full = ol.fill_B(o, N, S)
+    X = [np.ascontiguousarray(full[r::G]) for r in range(G)]
+    Y = [np.full_like(X[0], 0xDEADBEEF) for _ in range(G)]
+    yp, xp = _ptr_array(Y), _ptr_array(X)
+    for r in range(G):
+        assert f(X[r].ctypes.data, yp, N, G, r, S, S, inverse, 0) == 0
+    for x in X:
+        x[:] = 0xDEADBEEF
+    for r in range(G):
+        assert f(Y[r].ctypes.data, xp, N, G, r, S, S, inverse, 1) == 0
+    out = np.empty_like(full)
+    for r in range(G):
+        out[r::G] = X[r]
+    assert np.array_equal(out, ol.o_ntt(o, full, bool(inverse)))
+
+
 def test_p2p_rejects_unsupported_shapes():
     _build_emulator()
     emu = ctypes.CDLL(EMU)
