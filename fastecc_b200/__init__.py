@@ -58,6 +58,10 @@ def lib() -> ctypes.CDLL:
         L.fastecc_b200_gf_mul_dev.argtypes = [vp, vp, vp, sz, vp]; L.fastecc_b200_gf_mul_dev.restype = ci
         L.fastecc_b200_gf_inv_dev.argtypes = [vp, vp, sz, vp]; L.fastecc_b200_gf_inv_dev.restype = ci
         L.fastecc_b200_row_scale_dev.argtypes = [vp, sz, sz, sz, vp, vp]; L.fastecc_b200_row_scale_dev.restype = ci
+        L.fastecc_b200_rs_decode_pattern.argtypes = [sz, vp, sz, vp, ctypes.POINTER(vp)]; L.fastecc_b200_rs_decode_pattern.restype = ci
+        L.fastecc_b200_rs_decode_recover.argtypes = [vp, vp, sz, sz, vp, sz, vp]; L.fastecc_b200_rs_decode_recover.restype = ci
+        L.fastecc_b200_rs_decode_count.argtypes = [vp]; L.fastecc_b200_rs_decode_count.restype = sz
+        L.fastecc_b200_rs_decode_free.argtypes = [vp]; L.fastecc_b200_rs_decode_free.restype = None
         L.fastecc_b200_rs_encode_shard_pass.argtypes = [vp, sz, ci, ci, sz, sz, ci, vp]; L.fastecc_b200_rs_encode_shard_pass.restype = ci
         L.fastecc_b200_rs_encode_shard_pass_p2p.argtypes = [vp, vp, sz, ci, ci, sz, sz, ci, vp]; L.fastecc_b200_rs_encode_shard_pass_p2p.restype = ci
         L.fastecc_b200_ntt_shard_pass_p2p.argtypes = [vp, vp, sz, ci, ci, sz, sz, ci, ci, vp]; L.fastecc_b200_ntt_shard_pass_p2p.restype = ci

@@ -290,6 +290,17 @@ int run_host(uint32_t** data, size_t N, size_t size, int mode, const char* who)
 
 } // namespace
 
+// internal accessors for the other translation units of the library (decode.cu)
+namespace fecc {
+const uint4* context_power_table() { return g_ctx ? g_ctx->d_tw : nullptr; }
+int context_num_sms() { return g_ctx ? g_ctx->num_sms : 0; }
+int api_fail(int code, const char* fmt, ...)
+{
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+    return code;
+}
+}
+
 extern "C" {
 
 int fastecc_b200_init(int device)

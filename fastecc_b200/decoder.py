@@ -161,6 +161,49 @@ class ErasurePattern:
         return rec
 
 
+class CErasurePattern:
+    """The same decoder through the C ABI (fastecc_b200_rs_decode_pattern / _recover: csrc/decode.cu): what a C++ host uses.
+    Locator, its values and derivative values are built on the device in one call; recover() is asynchronous."""
+
+    def __init__(self, n2: int, erased):
+        import ctypes
+        import numpy as np
+        import torch
+        import fastecc_b200 as fe
+        self._fe, self._lib = fe, fe.lib()
+        fe.init(torch.cuda.current_device())
+        pos = np.ascontiguousarray(np.asarray(erased, dtype=np.int64))
+        if pos.size and (pos.min() < 0 or pos.max() >= (1 << 32)):
+            raise ValueError("erased: positions in [0, 2N)")
+        pos = pos.astype(np.uint32)
+        h = ctypes.c_void_p()
+        fe._check(self._lib.fastecc_b200_rs_decode_pattern(n2, pos.ctypes.data, pos.size, torch.cuda.current_stream().cuda_stream, ctypes.byref(h)))
+        self._h, self.n2, self.me = h, n2, int(pos.size)
+
+    def recover(self, code):
+        """code: [2N, S] int32 CUDA tensor (S % 4 == 0 or padded rows), DESTROYED.  Returns the [len(erased), S] recovered rows."""
+        import torch
+        if code.shape[0] != self.n2:
+            raise ValueError("code word has %d rows, the pattern was built for %d" % (code.shape[0], self.n2))
+        S = code.shape[1]
+        out = torch.empty((self.me, (S + 3) // 4 * 4), dtype=torch.int32, device=code.device)
+        if self.me:
+            self._fe._check(self._lib.fastecc_b200_rs_decode_recover(self._h, code.data_ptr(), S, code.stride(0), out.data_ptr(), out.stride(0),
+                                                                    torch.cuda.current_stream(code.device).cuda_stream))
+        return out[:, :S]
+
+    def close(self):
+        if self._h:
+            self._lib.fastecc_b200_rs_decode_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:            # noqa: BLE001 -- interpreter shutdown
+            pass
+
+
 def decode(code, erased, be=None):
     """One-shot form: build the pattern, recover the erased rows of `code` (destroyed)."""
     return ErasurePattern(code.shape[0], erased, code.device, be).recover(code)

@@ -108,6 +108,26 @@ int fastecc_b200_gf_mul_dev(const uint32_t* d_a, const uint32_t* d_b, uint32_t* 
 int fastecc_b200_gf_inv_dev(const uint32_t* d_a, uint32_t* d_out, size_t n, void* stream);
 int fastecc_b200_row_scale_dev(uint32_t* d_blocks, size_t n_rows, size_t SIZE_words, size_t pitch_words, const uint32_t* d_consts, void* stream);
 
+/* ---- erasure decoding --------------------------------------------------------------------------------
+ * The reference describes the decoder and does not implement it (README.md:88-119 "Fastest", RS.md:42-79, roadmap
+ * README.md:173).  Code word of 2N rows: row 2i = data block i, row 2j+1 = parity block j of fastecc_b200_rs_encode
+ * (RS.cpp:22-68).  Any set of at most N lost rows is recovered from the others by the formal-derivative method on two
+ * order-2N transforms of the hot path.
+ *   _pattern: everything that depends only on WHICH rows are lost (erasure locator by a product tree of batched transforms,
+ *             its values and derivative values), built on the device once; erased = HOST array of ascending distinct row
+ *             numbers < n_rows; n_rows = 2N = 2 .. 2^20, n_erased <= N.  Synchronises the stream.
+ *   _recover: d_code = the 2N rows (pitch_words per row, first SIZE_words meaningful, 16-byte aligned, pitch % 4 == 0; content
+ *             of the lost rows arbitrary); it is the workspace of the two transforms and is DESTROYED.  Row i of d_out
+ *             (out_pitch_words per row) receives lost row erased[i], canonical residues.  Asynchronous on the stream.
+ * A pattern may be used for any number of code words / columns.  Not pinned by reference code (there is none): checked
+ * against interpolation by definition and by encode -> erase -> decode round trips (tests/test_decoder.py). */
+typedef struct fastecc_b200_erasures fastecc_b200_erasures;
+int    fastecc_b200_rs_decode_pattern(size_t n_rows, const uint32_t* erased, size_t n_erased, void* stream, fastecc_b200_erasures** pattern);
+int    fastecc_b200_rs_decode_recover(const fastecc_b200_erasures* pattern, uint32_t* d_code, size_t SIZE_words, size_t pitch_words,
+                                      uint32_t* d_out, size_t out_pitch_words, void* stream);
+size_t fastecc_b200_rs_decode_count(const fastecc_b200_erasures* pattern);        /* n_erased */
+void   fastecc_b200_rs_decode_free(fastecc_b200_erasures* pattern);
+
 /* ---- one transform sharded over several GPUs (one process per GPU; BASELINE config 4) ---------------------------
  * Global block i = l*n_ranks + rank is local block l (data in, parity out).  An encode is: pass 0 on every rank,
  * all-to-all of whole blocks, pass 1, all-to-all, pass 2 -- the exchange is the caller's (fastecc_b200/sharded.py does it

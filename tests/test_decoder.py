@@ -131,3 +131,62 @@ def test_gpu_full_size_encode_erase_decode(fecc, oracle):
     code[erased] = -1
     rec = decoder.decode(code, erased.cpu().tolist(), decoder.CudaBackend())
     assert bool((rec == want).all())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,S,n_erased", [(1, 4, 1), (4, 8, 3), (16, 4, 16), (32, 8, 5), (64, 16, 40), (1024, 64, 1024), (4096, 32, 3000), (1 << 15, 16, 1 << 15)])
+def test_gpu_c_abi_decoder_recovers_erased_blocks(fecc, oracle, N, S, n_erased):
+    """fastecc_b200_rs_decode_pattern / _recover (csrc/decode.cu): the decoder a C++ host calls."""
+    import torch
+    from fastecc_b200 import decoder
+    code, rng = _codeword(oracle, N, S, 2000 + N)
+    erased = sorted(rng.choice(2 * N, size=n_erased, replace=False).tolist())
+    damaged = code.copy()
+    damaged[erased] = 0xDEADBEEF
+    pat = decoder.CErasurePattern(2 * N, erased)
+    for _ in range(2):                                           # a pattern serves any number of code words
+        rec = pat.recover(torch.from_numpy(damaged.view(np.int32)).cuda()).cpu().numpy().view(np.uint32)
+        assert np.array_equal(rec, code[erased])
+    pat.close()
+    if N <= 16:
+        want = decode_oracle.recover([[int(v) for v in r] for r in code], erased)
+        for k, e in enumerate(erased):
+            assert [int(v) for v in rec[k]] == want[e]
+
+
+@pytest.mark.gpu
+def test_gpu_c_abi_decoder_rejects_bad_patterns(fecc):
+    from fastecc_b200 import decoder
+    for n2, bad in ((16, [3, 3]), (16, [5, 2]), (16, [16]), (16, list(range(9))), (12, [1])):
+        with pytest.raises(fecc.FastEccError):
+            decoder.CErasurePattern(n2, bad)
+
+
+@pytest.mark.gpu
+def test_gpu_c_abi_full_size_encode_erase_decode(fecc, oracle):
+    """2^19 data + 2^19 parity blocks of 1 KiB, half of the code word erased at random: encoder and C-ABI decoder."""
+    import time
+    import torch
+    from fastecc_b200 import decoder
+    N, S = 1 << 19, 256
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    data = torch.randint(0, P, (N, S), device="cuda", generator=g, dtype=torch.int64).to(torch.int32)
+    par = data.clone()
+    fecc.rs_encode_dev(par)
+    code = torch.empty((2 * N, S), dtype=torch.int32, device="cuda")
+    code[0::2] = data
+    code[1::2] = par
+    del par
+    perm = torch.randperm(2 * N, device="cuda", generator=g)
+    erased = torch.sort(perm[:N]).values
+    want = code[erased].clone()
+    code[erased] = -1
+    pos = erased.cpu().tolist()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    pat = decoder.CErasurePattern(2 * N, pos)
+    torch.cuda.synchronize(); t1 = time.perf_counter()
+    rec = pat.recover(code)
+    torch.cuda.synchronize(); t2 = time.perf_counter()
+    print("C-ABI decoder, 2^19 of 2^20 rows erased: pattern %.1f ms (first use, incl. table builds), recover %.1f ms" % (1e3 * (t1 - t0), 1e3 * (t2 - t1)))
+    assert bool((rec == want).all())
+    pat.close()

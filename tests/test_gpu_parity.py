@@ -105,6 +105,37 @@ def test_host_api_at_pipelined_sizes(fecc, oracle, pin):
         del keep
 
 
+def test_elementwise_entry_points_match_oracle(fecc, oracle):
+    """fastecc_b200_gf_mul_dev / _gf_inv_dev / _row_scale_dev directly against GF_Mul / GF_Inv of the oracle (GF(p).cpp:110-127,
+    293-297), including non-canonical operands, 0, 1, P-1 and the values around P."""
+    import torch
+    rng = np.random.default_rng(3)
+    edge = np.array([0, 1, 2, P - 2, P - 1, P, P + 1, 0xFFFFFFFF, 0x80000000, 0xFFF00000, 0x000FFFFF], dtype=np.uint32)
+    a = np.concatenate([np.repeat(edge, len(edge)), rng.integers(0, 1 << 32, size=5000, dtype=np.uint64).astype(np.uint32)])
+    b = np.concatenate([np.tile(edge, len(edge)), rng.integers(0, 1 << 32, size=5000, dtype=np.uint64).astype(np.uint32)])
+    L = fecc.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    ta, tb = to_dev(a), to_dev(b)
+    out = torch.empty_like(ta)
+    fecc._check(L.fastecc_b200_gf_mul_dev(ta.data_ptr(), tb.data_ptr(), out.data_ptr(), ta.numel(), st))
+    want = np.array([oracle.oracle_gf_mul(int(x) % P, int(y) % P) for x, y in zip(a, b)], dtype=np.uint32)
+    assert np.array_equal(to_host(out), want)
+    fecc._check(L.fastecc_b200_gf_inv_dev(ta.data_ptr(), out.data_ptr(), ta.numel(), st))
+    got = to_host(out)
+    want = np.array([oracle.oracle_gf_inv(int(x) % P) if int(x) % P else 0 for x in a], dtype=np.uint32)
+    assert np.array_equal(got, want)
+    assert all(oracle.oracle_gf_mul(int(g), int(x) % P) == 1 for g, x in zip(got[:300], a[:300]) if int(x) % P)
+    rows, S, pitch = 77, 36, 40                                            # row i *= c[i]  (the shape of RS.cpp:51-59)
+    blk = rng.integers(0, 1 << 32, size=(rows, pitch), dtype=np.uint64).astype(np.uint32)
+    c = rng.integers(0, 1 << 32, size=rows, dtype=np.uint64).astype(np.uint32)
+    c[:len(edge)] = edge
+    tblk, tc = to_dev(blk), to_dev(c)
+    fecc._check(L.fastecc_b200_row_scale_dev(tblk.data_ptr(), rows, S, pitch, tc.data_ptr(), st))
+    got = to_host(tblk)
+    want = ((blk[:, :S].astype(np.uint64) % P) * (c.astype(np.uint64)[:, None] % P) % P).astype(np.uint32)
+    assert np.array_equal(got[:, :S], want) and np.array_equal(got[:, S:], blk[:, S:])
+
+
 def test_host_scattered_blocks(fecc, oracle):
     """Blocks at arbitrary addresses, in permuted order (the reference leaves its own table permuted)."""
     N, S = 64, 12
