@@ -24,8 +24,15 @@ if len(sys.argv) > 2:
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(src)))
     secs = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
+    # ncu prints the source page of a launch more than once (one copy per source view); keep one section per launch
+    sections = []
+    for a, b in zip(secs[:-1], secs[1:]):
+        sec = rows[a:b]
+        if not sections or sec != sections[-1]:
+            sections.append(sec)
     which = int(sys.argv[2])
-    s = secs[which]; h = rows[s + 1]; body = rows[s + 2:secs[which + 1]]
+    sec = sections[which]; h = sec[1]; body = sec[2:]
+    print("\n" + " ".join(sec[0][:2]))
     ci = {x: i for i, x in enumerate(h)}
     stalls = [x for x in h if x.startswith("stall_") and "Not Issued" not in x]
     tot = sum(int(r[ci["# Samples"]]) for r in body)
