@@ -536,6 +536,16 @@ int fastecc_b200_ntt_shard_pass_p2p(const uint32_t* d_src, uint32_t* const* d_pe
     return 0;
 }
 
+int fastecc_b200_shard_barrier(uint32_t* const* d_flag_peers, int n_ranks, int rank, uint32_t epoch, void* stream)
+{
+    const char* who = "fastecc_b200_shard_barrier";
+    if (!g_ctx) return fail(FASTECC_B200_ENOINIT, "%s: call fastecc_b200_init() first", who);
+    if (!d_flag_peers || n_ranks < 1 || n_ranks > 8 || rank < 0 || rank >= n_ranks) return fail(FASTECC_B200_EINVAL, "%s: bad arguments", who);
+    for (int r = 0; r < n_ranks; ++r) if (!d_flag_peers[r]) return fail(FASTECC_B200_EINVAL, "%s: flag array of rank %d missing", who, r);
+    CUDA_TRY(launch_shard_barrier(d_flag_peers, (uint32_t)n_ranks, (uint32_t)rank, epoch, (cudaStream_t)stream)); g_launches++;
+    return 0;
+}
+
 // Device buffers that can be mapped into the other ranks' address spaces (cudaMalloc + CUDA IPC: torch's caching
 // allocator hands out sub-blocks, which cannot be exported).
 void* fastecc_b200_dev_alloc(size_t bytes)

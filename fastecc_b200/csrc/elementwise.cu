@@ -48,6 +48,39 @@ __global__ void __launch_bounds__(256) row_scale_kernel(uint4* __restrict__ d, s
     }
 }
 
+// Cross-GPU barrier on a stream (one process per GPU, buffers mapped with CUDA IPC): rank r owns an array of n_ranks 32-bit
+// flags.  Lane p of one warp writes `epoch` into flag [rank] of peer p (over NVLink) and then waits until its own flag [p]
+// has reached `epoch`.  The kernel runs behind the pass whose peer stores it has to publish: those are complete when it
+// starts (stream order), the fence orders them before the flag.  A peer that never arrives would spin forever, so the wait
+// gives up after about ten seconds and reports through *err (the next host-side check fails loudly instead of hanging).
+struct BarrierArgs { uint32_t* peers[8]; };
+__global__ void shard_barrier_kernel_args(BarrierArgs a, const uint32_t* own, uint32_t n_ranks, uint32_t rank, uint32_t epoch, uint32_t* err)
+{
+    const uint32_t p = threadIdx.x;
+    if (p >= n_ranks) return;
+    __threadfence_system();
+    volatile uint32_t* remote = a.peers[p] + rank;
+    *remote = epoch;
+    __threadfence_system();
+    const volatile uint32_t* mine = own + p;
+    const long long t0 = clock64();
+    while ((int32_t)(*mine - epoch) < 0) {
+        if (clock64() - t0 > 20000000000ll) { atomicExch(err, 1u); break; }
+        __nanosleep(100);
+    }
+    __threadfence_system();
+}
+
+cudaError_t launch_shard_barrier(uint32_t* const* host_peers, uint32_t n_ranks, uint32_t rank, uint32_t epoch, cudaStream_t st)
+{
+    if (n_ranks > 8 || rank >= n_ranks) return cudaErrorInvalidValue;
+    BarrierArgs a;
+    for (uint32_t r = 0; r < 8; ++r) a.peers[r] = host_peers[r < n_ranks ? r : 0];
+    // flag layout of a rank: [0, 8) arrival flags, [8] error word
+    shard_barrier_kernel_args<<<1, 32, 0, st>>>(a, host_peers[rank], n_ranks, rank, epoch, host_peers[rank] + 8);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_gf_mul(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, cudaStream_t st)
 {
     if (!n) return cudaSuccess;

@@ -3,7 +3,8 @@
 Two implementations of the same decomposition:
   * P2PShardedEncoder -- the exchange is FUSED into the pass kernels: passes A and BC store every output row straight
     into the memory of the GPU that owns it (CUDA IPC mappings, NVLink), so there is no all-to-all, no pack/unpack
-    and no extra trip through HBM; the passes are separated by a one-word NCCL all-reduce (a stream-ordered barrier).
+    and no extra trip through HBM; the passes are separated by a flag barrier over the same peer mappings (a one-warp
+    kernel on the stream, fastecc_b200_shard_barrier).  torch.distributed only carries the IPC handles at set-up.
   * rs_encode_sharded -- local passes + two NCCL all-to-alls of whole blocks (the plain-library baseline; also what the
     CPU/gloo tests run, with the kernel emulated).
 
@@ -110,6 +111,9 @@ def p2p_ntt_supported(N: int, G: int) -> bool:
     return bool(_support_bits(N, G) & 2)
 
 
+BARRIER_WORDS = 16                    # include/fastecc_b200.h FASTECC_B200_BARRIER_WORDS
+
+
 class _RawCudaBuffer:
     """A cudaMalloc'ed block exposed through __cuda_array_interface__ (torch.as_tensor keeps this object alive)."""
     def __init__(self, ptr: int, shape, typestr="<i4"):
@@ -123,12 +127,16 @@ class P2PShardedEncoder:
     call enc.encode(), read the local parity blocks from the same tensor.  Collective: every rank constructs it and calls
     encode() the same number of times.  One process per GPU on one node (CUDA IPC)."""
 
-    def __init__(self, N: int, S: int, group=None):
+    def __init__(self, N: int, S: int, group=None, barrier: str = "flags"):
+        """barrier: "flags" (default: fastecc_b200_shard_barrier, a kernel over the peer mappings) or "nccl" (a one-word all-reduce)."""
         import ctypes
         import torch
         import torch.distributed as dist
         import fastecc_b200 as fe
         self.N, self.S, self.group = N, S, group
+        if barrier not in ("flags", "nccl"):
+            raise ValueError("barrier must be 'flags' or 'nccl'")
+        self.barrier_kind = barrier
         self.G, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self._can_encode, self._can_ntt = p2p_supported(N, self.G), p2p_ntt_supported(N, self.G)
         if not (self._can_encode or self._can_ntt) or S % 4:
@@ -138,22 +146,27 @@ class P2PShardedEncoder:
         fe.init(self._dev)
         rows = N // self.G
         nbytes = rows * S * 4
-        self._own = [L.fastecc_b200_dev_alloc(nbytes), L.fastecc_b200_dev_alloc(nbytes)]          # X, Y
+        self._own = [L.fastecc_b200_dev_alloc(nbytes), L.fastecc_b200_dev_alloc(nbytes), L.fastecc_b200_dev_alloc(4 * BARRIER_WORDS)]     # X, Y, barrier flags
         if not all(self._own):
             raise MemoryError(L.fastecc_b200_last_error().decode())
-        handles = torch.empty(128, dtype=torch.uint8)
-        hb = (ctypes.c_ubyte * 128)()
-        for k in range(2):
+        self._flags = torch.as_tensor(_RawCudaBuffer(self._own[2], (BARRIER_WORDS,)), device=torch.device("cuda", self._dev))
+        self._flags.zero_()
+        torch.cuda.synchronize()                                       # the flags are zero before anybody can reach them
+        self._epoch = 0
+        nh = len(self._own)
+        handles = torch.empty(64 * nh, dtype=torch.uint8)
+        hb = (ctypes.c_ubyte * (64 * nh))()
+        for k in range(nh):
             fe._check(L.fastecc_b200_ipc_export(self._own[k], ctypes.addressof(hb) + 64 * k))
         handles.copy_(torch.frombuffer(bytearray(hb), dtype=torch.uint8))
         dev_handles = handles.cuda()
-        everyone = torch.empty(128 * self.G, dtype=torch.uint8, device=dev_handles.device)
+        everyone = torch.empty(64 * nh * self.G, dtype=torch.uint8, device=dev_handles.device)
         dist.all_gather_into_tensor(everyone, dev_handles, group=group)
-        everyone = everyone.cpu().numpy().reshape(self.G, 2, 64)
+        everyone = everyone.cpu().numpy().reshape(self.G, nh, 64)
         self._opened = []
-        peers = [[0] * self.G, [0] * self.G]
+        peers = [[0] * self.G for _ in range(nh)]
         for r in range(self.G):
-            for k in range(2):
+            for k in range(nh):
                 if r == self.rank:
                     peers[k][r] = self._own[k]
                 else:
@@ -161,16 +174,34 @@ class P2PShardedEncoder:
                     fe._check(L.fastecc_b200_ipc_open(everyone[r, k].ctypes.data, ctypes.byref(p)))
                     peers[k][r] = p.value
                     self._opened.append(p.value)
-        self._peers = peers                                            # [X or Y][rank] -> device address in this process
+        self._peers = peers                                            # [X, Y or flags][rank] -> device address in this process
+        self._flag_peers = (ctypes.c_void_p * self.G)(*peers[2])
         self._ptr_cache = {}
         self.x = torch.as_tensor(_RawCudaBuffer(self._own[0], (rows, S)), device=torch.device("cuda", self._dev))
         self._flag = torch.zeros(1, dtype=torch.int32, device=self.x.device)
         self._s_h2d = self._s_d2h = None
-        self._barrier()                                                # nobody stores into a peer before everybody has mapped everything
+        self._nccl_barrier()                                           # nobody stores into a peer before everybody has mapped everything
+
+    def _nccl_barrier(self):
+        import torch.distributed as dist
+        dist.all_reduce(self._flag, group=self.group)                  # set-up / tear-down only
 
     def _barrier(self):
-        import torch.distributed as dist
-        dist.all_reduce(self._flag, group=self.group)                  # on the current stream: orders the passes of all ranks
+        """Orders the passes of all ranks on the current stream: a one-warp kernel that raises this rank's flag in every peer and
+        waits for theirs (fastecc_b200_shard_barrier) -- no NCCL and no host involvement on the data path."""
+        import torch
+        import fastecc_b200 as fe
+        if self.barrier_kind == "nccl":
+            return self._nccl_barrier()
+        self._epoch += 1
+        fe._check(self._lib.fastecc_b200_shard_barrier(self._flag_peers, self.G, self.rank, self._epoch & 0xFFFFFFFF, torch.cuda.current_stream().cuda_stream))
+
+    def check(self):
+        """Raise if a barrier ever timed out (a peer died or fell out of step).  Synchronises the device."""
+        import torch
+        torch.cuda.synchronize()
+        if int(self._flags[8].item()) != 0:
+            raise RuntimeError("fastecc_b200 sharded barrier timed out on rank %d: the ranks are out of step" % self.rank)
 
     def _peer_arrays(self, off_bytes: int):
         """HOST arrays of the peers' X and Y addresses, shifted to a column offset (column chunks are independent codewords)."""
@@ -211,13 +242,14 @@ class P2PShardedEncoder:
 
     def ntt(self, inverse: bool = False, events=None):
         """ONE standalone transform of the N blocks (MFA_NTT, ntt.cpp:382-447; unnormalised inverse), in place in enc.x, cyclic
-        blocks in and out: pass A' stores into the owners' Y over NVLink, one barrier, pass B' is local.  events: 4 CUDA events."""
+        blocks in and out: pass A' stores into the owners' Y over NVLink, barrier, pass B' is local, barrier (nobody may overwrite a Y
+        its owner is still reading; the encode's passes have that barrier between BC and D already).  events: 4 CUDA events."""
         import torch
         import fastecc_b200 as fe
         if not self._can_ntt:
             raise ValueError("N = %d cannot be transformed over %d ranks with the fused exchange" % (self.N, self.G))
         L, st = self._lib, torch.cuda.current_stream().cuda_stream
-        X, Y = self._own
+        X, Y = self._own[:2]
         xp, yp = self._peer_arrays(0)
 
         def mark():
@@ -230,6 +262,7 @@ class P2PShardedEncoder:
         mark()
         fe._check(L.fastecc_b200_ntt_shard_pass_p2p(Y, xp, self.N, self.G, self.rank, self.S, self.S, 1 if inverse else 0, 1, st))
         mark()
+        self._barrier()                        # the next operation's first pass stores into the peers' Y: they must be done reading it
         return self.x
 
     def encode_host(self, h_in, h_out=None, chunk_words: int = 256):
@@ -267,10 +300,13 @@ class P2PShardedEncoder:
         import torch
         if self._own:
             torch.cuda.synchronize()
-            self._barrier(); torch.cuda.synchronize()                  # no peer is still storing into our buffers
+            self._nccl_barrier(); torch.cuda.synchronize()             # no peer is still storing into our buffers
+            timed_out = int(self._flags[8].item()) != 0
             for p in self._opened:
                 self._lib.fastecc_b200_ipc_close(p)
-            self.x = None
+            self.x = self._flags = None
             for p in self._own:
                 self._lib.fastecc_b200_dev_free(p)
             self._own, self._opened = [], []
+            if timed_out:
+                raise RuntimeError("fastecc_b200 sharded barrier timed out on rank %d: the ranks were out of step, results are invalid" % self.rank)

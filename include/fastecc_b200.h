@@ -143,10 +143,19 @@ int fastecc_b200_rs_encode_shard_pass(uint32_t* d_local, size_t N, int n_ranks, 
  *   which 1: reads the local Y, writes the rows of X on their owners     d_src = Y_local, d_peers[r] = rank r's X
  *   which 2: local, in place on X                                        d_src = X_local, d_peers[rank] = X_local
  * d_peers: HOST array of n_ranks device pointers (own buffer at [rank]).  The caller separates the passes with a
- * cross-rank barrier on the stream (fastecc_b200/sharded.py: a one-word NCCL all-reduce).  n_ranks = 2, 4 or 8; N = 2^12..2^19 with
+ * cross-rank barrier on the stream (fastecc_b200_shard_barrier below).  n_ranks = 2, 4 or 8; N = 2^12..2^19 with
  * both factors of N = N1*N2 (csrc/plan.h split_l1) at least 32*n_ranks, so that the 32 rows a thread stores go to one rank. */
 int fastecc_b200_rs_encode_shard_pass_p2p(const uint32_t* d_src, uint32_t* const* d_peers, size_t N, int n_ranks, int rank,
                                           size_t SIZE_words, size_t pitch_words, int which, void* stream);
+/* The cross-rank barrier between those passes, as a kernel on the stream (no NCCL, no host round trip): every rank owns an array
+ * of FASTECC_B200_BARRIER_WORDS zero-initialised words from fastecc_b200_dev_alloc, mapped into the peers like X and Y;
+ * d_flag_peers = HOST array of the n_ranks arrays (own at [rank]).  Rank r writes `epoch` into word [r] of every peer's array and
+ * waits until its own words [0, n_ranks) have reached it; epoch = 1, 2, 3, ... in the same order on every rank.  The kernel runs
+ * behind the pass whose peer stores it publishes.  A peer that never arrives makes it give up after about ten seconds and set
+ * word [8] of the own array (check it after synchronising; fastecc_b200/sharded.py raises). */
+#define FASTECC_B200_BARRIER_WORDS 16
+int fastecc_b200_shard_barrier(uint32_t* const* d_flag_peers, int n_ranks, int rank, uint32_t epoch, void* stream);
+
 /* ONE standalone transform (MFA_NTT, ntt.cpp:382-447; unnormalised inverse) sharded the same way: cyclic blocks in and out.
  *   which 0: reads the local X, stores into the Ys of the owners (the four-step transpose as peer stores)   d_src = X_local, d_peers[r] = rank r's Y
  *   which 1: local, Y -> X                                                                                  d_src = Y_local, d_peers[rank] = X_local
