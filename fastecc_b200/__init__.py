@@ -65,6 +65,8 @@ def lib() -> ctypes.CDLL:
         L.fastecc_b200_rs_encode_shard_pass.argtypes = [vp, sz, ci, ci, sz, sz, ci, vp]; L.fastecc_b200_rs_encode_shard_pass.restype = ci
         L.fastecc_b200_rs_encode_shard_pass_p2p.argtypes = [vp, vp, sz, ci, ci, sz, sz, ci, vp]; L.fastecc_b200_rs_encode_shard_pass_p2p.restype = ci
         L.fastecc_b200_ntt_shard_pass_p2p.argtypes = [vp, vp, sz, ci, ci, sz, sz, ci, ci, vp]; L.fastecc_b200_ntt_shard_pass_p2p.restype = ci
+        L.fastecc_b200_rs_encode_shard_p2p.argtypes = [vp, vp, vp, vp, sz, ci, ci, sz, sz, vp]; L.fastecc_b200_rs_encode_shard_p2p.restype = ci
+        L.fastecc_b200_ntt_shard_p2p.argtypes = [vp, vp, vp, vp, sz, ci, ci, sz, sz, ci, vp]; L.fastecc_b200_ntt_shard_p2p.restype = ci
         L.fastecc_b200_shard_barrier.argtypes = [vp, ci, ci, ctypes.c_uint32, vp]; L.fastecc_b200_shard_barrier.restype = ci
         L.fastecc_b200_dev_alloc.argtypes = [sz]; L.fastecc_b200_dev_alloc.restype = vp
         L.fastecc_b200_dev_free.argtypes = [vp]; L.fastecc_b200_dev_free.restype = None

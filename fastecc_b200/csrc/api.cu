@@ -546,6 +546,31 @@ int fastecc_b200_shard_barrier(uint32_t* const* d_flag_peers, int n_ranks, int r
     return 0;
 }
 
+// The whole sharded encode / transform of one rank as ONE call: the passes and the barriers between them, enqueued on the
+// stream.  *epoch is the rank's barrier counter (starts at 0, same sequence of calls on every rank).
+int fastecc_b200_rs_encode_shard_p2p(uint32_t* const* d_x_peers, uint32_t* const* d_y_peers, uint32_t* const* d_flag_peers, uint32_t* epoch,
+                                     size_t N, int n_ranks, int rank, size_t size, size_t pitch, void* stream)
+{
+    const char* who = "fastecc_b200_rs_encode_shard_p2p";
+    if (!d_x_peers || !d_y_peers || !d_flag_peers || !epoch || rank < 0 || rank >= n_ranks) return fail(FASTECC_B200_EINVAL, "%s: bad arguments", who);
+    if (int rc = fastecc_b200_rs_encode_shard_pass_p2p(d_x_peers[rank], d_y_peers, N, n_ranks, rank, size, pitch, 0, stream)) return rc;
+    if (int rc = fastecc_b200_shard_barrier(d_flag_peers, n_ranks, rank, ++*epoch, stream)) return rc;
+    if (int rc = fastecc_b200_rs_encode_shard_pass_p2p(d_y_peers[rank], d_x_peers, N, n_ranks, rank, size, pitch, 1, stream)) return rc;
+    if (int rc = fastecc_b200_shard_barrier(d_flag_peers, n_ranks, rank, ++*epoch, stream)) return rc;
+    return fastecc_b200_rs_encode_shard_pass_p2p(d_x_peers[rank], d_x_peers, N, n_ranks, rank, size, pitch, 2, stream);
+}
+
+int fastecc_b200_ntt_shard_p2p(uint32_t* const* d_x_peers, uint32_t* const* d_y_peers, uint32_t* const* d_flag_peers, uint32_t* epoch,
+                               size_t N, int n_ranks, int rank, size_t size, size_t pitch, int inverse, void* stream)
+{
+    const char* who = "fastecc_b200_ntt_shard_p2p";
+    if (!d_x_peers || !d_y_peers || !d_flag_peers || !epoch || rank < 0 || rank >= n_ranks) return fail(FASTECC_B200_EINVAL, "%s: bad arguments", who);
+    if (int rc = fastecc_b200_ntt_shard_pass_p2p(d_x_peers[rank], d_y_peers, N, n_ranks, rank, size, pitch, inverse, 0, stream)) return rc;
+    if (int rc = fastecc_b200_shard_barrier(d_flag_peers, n_ranks, rank, ++*epoch, stream)) return rc;
+    if (int rc = fastecc_b200_ntt_shard_pass_p2p(d_y_peers[rank], d_x_peers, N, n_ranks, rank, size, pitch, inverse, 1, stream)) return rc;
+    return fastecc_b200_shard_barrier(d_flag_peers, n_ranks, rank, ++*epoch, stream);      // nobody overwrites a Y its owner is still reading
+}
+
 // Device buffers that can be mapped into the other ranks' address spaces (cudaMalloc + CUDA IPC: torch's caching
 // allocator hands out sub-blocks, which cannot be exported).
 void* fastecc_b200_dev_alloc(size_t bytes)

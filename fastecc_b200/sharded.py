@@ -152,7 +152,7 @@ class P2PShardedEncoder:
         self._flags = torch.as_tensor(_RawCudaBuffer(self._own[2], (BARRIER_WORDS,)), device=torch.device("cuda", self._dev))
         self._flags.zero_()
         torch.cuda.synchronize()                                       # the flags are zero before anybody can reach them
-        self._epoch = 0
+        self._epoch = ctypes.c_uint32(0)                               # barrier counter, shared with the single-call C entry points
         nh = len(self._own)
         handles = torch.empty(64 * nh, dtype=torch.uint8)
         hb = (ctypes.c_ubyte * (64 * nh))()
@@ -193,8 +193,8 @@ class P2PShardedEncoder:
         import fastecc_b200 as fe
         if self.barrier_kind == "nccl":
             return self._nccl_barrier()
-        self._epoch += 1
-        fe._check(self._lib.fastecc_b200_shard_barrier(self._flag_peers, self.G, self.rank, self._epoch & 0xFFFFFFFF, torch.cuda.current_stream().cuda_stream))
+        self._epoch.value = (self._epoch.value + 1) & 0xFFFFFFFF
+        fe._check(self._lib.fastecc_b200_shard_barrier(self._flag_peers, self.G, self.rank, self._epoch.value, torch.cuda.current_stream().cuda_stream))
 
     def check(self):
         """Raise if a barrier ever timed out (a peer died or fell out of step).  Synchronises the device."""
@@ -235,9 +235,17 @@ class P2PShardedEncoder:
 
     def encode(self, events=None):
         """events: optional list that receives 6 CUDA events bracketing pass A, barrier, pass BC, barrier, pass D."""
+        import ctypes
+        import torch
+        import fastecc_b200 as fe
         if not self._can_encode:
             raise ValueError("N = %d cannot be encoded over %d ranks with the fused exchange" % (self.N, self.G))
-        self._passes(0, self.S, events)
+        if events is None and self.barrier_kind == "flags":            # the whole rank-local sequence as ONE C call
+            xp, yp = self._peer_arrays(0)
+            fe._check(self._lib.fastecc_b200_rs_encode_shard_p2p(xp, yp, self._flag_peers, ctypes.byref(self._epoch), self.N, self.G, self.rank,
+                                                                self.S, self.S, torch.cuda.current_stream().cuda_stream))
+        else:
+            self._passes(0, self.S, events)
         return self.x
 
     def ntt(self, inverse: bool = False, events=None):
@@ -248,9 +256,14 @@ class P2PShardedEncoder:
         import fastecc_b200 as fe
         if not self._can_ntt:
             raise ValueError("N = %d cannot be transformed over %d ranks with the fused exchange" % (self.N, self.G))
+        import ctypes
         L, st = self._lib, torch.cuda.current_stream().cuda_stream
         X, Y = self._own[:2]
         xp, yp = self._peer_arrays(0)
+        if events is None and self.barrier_kind == "flags":
+            fe._check(L.fastecc_b200_ntt_shard_p2p(xp, yp, self._flag_peers, ctypes.byref(self._epoch), self.N, self.G, self.rank, self.S, self.S,
+                                                   1 if inverse else 0, st))
+            return self.x
 
         def mark():
             if events is not None:

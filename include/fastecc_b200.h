@@ -156,6 +156,15 @@ int fastecc_b200_rs_encode_shard_pass_p2p(const uint32_t* d_src, uint32_t* const
 #define FASTECC_B200_BARRIER_WORDS 16
 int fastecc_b200_shard_barrier(uint32_t* const* d_flag_peers, int n_ranks, int rank, uint32_t epoch, void* stream);
 
+/* One rank's share of a whole sharded encode / transform as ONE call: the passes above and the barriers between them, enqueued
+ * on the stream.  d_x_peers / d_y_peers / d_flag_peers: HOST arrays of every rank's X, Y and barrier-flag buffers (own at [rank]);
+ * *epoch: this rank's barrier counter, 0 before the first call (the same sequence of calls on every rank).  This is all a C++ host
+ * needs for the multi-GPU path once the IPC handles are exchanged (integration/shard_example.cpp). */
+int fastecc_b200_rs_encode_shard_p2p(uint32_t* const* d_x_peers, uint32_t* const* d_y_peers, uint32_t* const* d_flag_peers, uint32_t* epoch,
+                                     size_t N, int n_ranks, int rank, size_t SIZE_words, size_t pitch_words, void* stream);
+int fastecc_b200_ntt_shard_p2p(uint32_t* const* d_x_peers, uint32_t* const* d_y_peers, uint32_t* const* d_flag_peers, uint32_t* epoch,
+                               size_t N, int n_ranks, int rank, size_t SIZE_words, size_t pitch_words, int inverse, void* stream);
+
 /* ONE standalone transform (MFA_NTT, ntt.cpp:382-447; unnormalised inverse) sharded the same way: cyclic blocks in and out.
  *   which 0: reads the local X, stores into the Ys of the owners (the four-step transpose as peer stores)   d_src = X_local, d_peers[r] = rank r's Y
  *   which 1: local, Y -> X                                                                                  d_src = Y_local, d_peers[rank] = X_local

@@ -229,3 +229,25 @@ def test_p2p_fused_exchange_headline_hash_all_gpus():
 @pytest.mark.parametrize("L,S", [(11, 64), (16, 1024)])
 def test_sharded_encode_on_gpus(L, S):
     _run(_worker, L, S)
+
+
+def test_cpp_host_drives_the_sharded_encode(tmp_path):
+    """integration/shard_example.cpp: one process per GPU, plain C++ on the C ABI (IPC handles exchanged through files, the
+    passes and barriers through fastecc_b200_rs_encode_shard_p2p); every rank's parity rows must hash like the oracle's."""
+    import subprocess
+    import torch
+    import oracle_lib as ol
+    import fastecc_b200 as fe
+    exe = os.path.join(ROOT, "integration", "shard_example")
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2 or not os.path.exists(exe):
+        pytest.skip("needs at least 2 GPUs and the built example (python __graft_entry__.py)")
+    world = 1 << (world.bit_length() - 1)
+    L, S = 16, 64
+    procs = [subprocess.Popen([exe, str(r), str(world), str(L), str(S), str(tmp_path)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(world)]
+    outs = [p.communicate(timeout=240) for p in procs]
+    assert all(p.returncode == 0 for p in procs), [o[1][-500:] for o in outs]
+    o = ol.load_oracle()
+    want = ol.o_encode(o, ol.fill_A(o, 1 << L, S))
+    for r in range(world):
+        assert ("local hash %d" % fe.reference_hash(np.ascontiguousarray(want[r::world]))) in outs[r][0], outs[r][0]
