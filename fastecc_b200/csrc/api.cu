@@ -173,7 +173,7 @@ int run_aligned(Context* c, uint32_t* x, size_t N, size_t size, size_t pitch, in
         return 0;
     }
     Buffers b{x, nullptr, c->d_tw, (uint32_t)pitch, (uint32_t)size};
-    const bool need_y = mode != 2 && N > ((size_t)1 << kMaxLogR);
+    const bool need_y = mode != 2 && !single_pass(ilog2(N));               // the two-pass NTT ping-pongs through Y
     if (need_y) {
         std::lock_guard<std::mutex> lk(g_mu);
         CUDA_TRY(c->scratch.acquire(N * pitch * sizeof(uint32_t), st));

@@ -9,16 +9,16 @@
 // result is the unique canonical DFT, so the split is ours to choose.  Here N = N1*N2 with both factors <= 1024
 // (one 64 KiB shared-memory tile holds a whole length-N1 or length-N2 column strip):
 //
-//   NTT  (N > 1024, out of place through a scratch buffer Y so that natural order comes out without a transpose pass):
+//   NTT  (N >= 1024, out of place through a scratch buffer Y so that natural order comes out without a transpose pass):
 //     A'  X -> Y : for each n2, DIT over n1 (rows n1*N2+n2), plain; element k1 goes to row n2*N1+k1
 //     B'  Y -> X : for each k1, DIT over n2 (rows n2*N1+k1) with input twist (w^k1)^n2; k2 goes to row k1+N1*k2
-//   ENCODE (N > 1024, in place, 3 passes instead of 2+2; m = k1 + N1*k2 is the coefficient index):
+//   ENCODE (N >= 1024, in place, 3 passes instead of 2+2; m = k1 + N1*k2 is the coefficient index):
 //     A   for each n2, inverse DIT over n1 (rows n1*N2+n2), inputs pre-scaled by 1/N
 //     BC  for each k1 (rows k1*N2+.., contiguous): inverse DIT over n2 with input twist (w^-k1)^n2, then
 //         forward DIT over k2 with input twist (rho^N1)^k2          (rho = root_2N, RS.cpp:51)
 //     D   for each j2, forward DIT over k1 (rows k1*N2+j2) with input twist (w^j2 * rho)^k1 -> parity row j1*N2+j2
 //   so the four-step twiddles (ntt.cpp:421-431) and the scaling rho^m (RS.cpp:54-58) never cost a multiplication.
-//   N <= 1024: a single pass (NTT) or a single fused pass (encode).   N < 32: see small_dft.cu.
+//   N <= 512: a single pass (NTT) or a single fused pass (encode).   N < 32: see small_dft.cu.
 #pragma once
 #include <vector>
 #include <stdint.h>
@@ -46,6 +46,12 @@ inline uint32_t split_l1(uint32_t LN)
     if (LN - L1 > (uint32_t)kMaxLogR) L1 = LN - kMaxLogR;
     return L1;
 }
+
+// Orders up to 2^9 run as ONE pass (the whole transform, or the whole fused encode, on a tile).  2^10 could too (a tile holds 1024
+// rows), but its 4 MiB at 4 KiB blocks are then only 64 tiles each doing 10 (NTT) or 20 (encode) stages in series: 30 / 53 us,
+// slower than 2^11 with its two / three short passes (16 / 32 us).  So 2^10 = 32 x 32 takes the multi-pass plans as well.
+constexpr uint32_t kSinglePassMaxLog = 9;
+inline bool single_pass(uint32_t LN) { return LN <= kSinglePassMaxLog; }
 
 struct Buffers { uint32_t* x; uint32_t* y; const uint4* tw; uint32_t pitch_words; uint32_t size_words; };
 
@@ -78,7 +84,7 @@ inline std::vector<PassParams> plan_ntt(const Buffers& b, size_t N, bool inverse
     std::vector<PassParams> v;
     const uint32_t LN = ilog2(N);
     const long long p = (long long)(kM / N) * (inverse ? -1 : 1);       // w = g^p
-    if (LN <= kMaxLogR) {
+    if (single_pass(LN)) {
         PassParams a = base_pass(b, LN);
         a.src = b.x; a.dst = b.x; a.nsets = 1;
         a.src_set_stride = a.dst_set_stride = 0; a.src_row_stride = a.dst_row_stride = 1;
@@ -112,7 +118,7 @@ inline std::vector<PassParams> plan_encode(const Buffers& b, size_t N)
     const uint32_t LN = ilog2(N);
     const long long q = (long long)(kM / (2 * N));                      // rho = root_2N = g^q, w = g^(2q)
     const uint32_t invN = gf::inv((uint32_t)N);                         // GF_Inv(N), RS.cpp:51
-    if (LN <= kMaxLogR) {
+    if (single_pass(LN)) {
         PassParams a = base_pass(b, LN);
         a.src = b.x; a.dst = b.x; a.nsets = 1;
         a.src_set_stride = a.dst_set_stride = 0; a.src_row_stride = a.dst_row_stride = 1;

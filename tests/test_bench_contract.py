@@ -43,3 +43,26 @@ def test_b200_arm_without_a_gpu_fails_loudly():
     r = _run(["--steps", "1", "--warmup", "1", "--no-cpu-baseline", "--no-e2e"], env={"CUDA_VISIBLE_DEVICES": ""})
     assert r.returncode != 0
     assert r.stdout.strip() == ""                      # nothing that could be mistaken for a measurement
+
+
+def test_fill_a_rows_is_the_reference_fill_dealt_cyclically():
+    """bench.py fills every rank's shard directly (global block l*G + rank = local row l of data0[i] = i % P, RS.cpp:28-29)."""
+    import importlib.util
+    import numpy as np
+    import torch
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    N, S, G = 64, 12, 4
+    full = (np.arange(N * S, dtype=np.uint64) % bench.P).astype(np.uint32).reshape(N, S)
+    for r in range(G):
+        got = bench.fill_a_rows(torch, "cpu", r, G, N // G, S).numpy().view(np.uint32)
+        assert np.array_equal(got, full[r::G])
+    assert bench.GOLDEN_PARITY_HASH_FILL_A[(19, 1024)] == 4272226309       # SURVEY 8c
+    class A: log_n = 19; block_bytes = 4096
+    assert bench.check_golden(A, 4272226309, "x")["golden_match"] is True
+    try:
+        bench.check_golden(A, 1, "x")
+        assert False, "a wrong hash must abort the run"
+    except SystemExit as e:
+        assert "PARITY FAILURE" in str(e)
