@@ -5,6 +5,7 @@
 #include "small_dft.h"
 #include "byte_recode.h"
 #include "elementwise.h"
+#include "mixed_radix.h"
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdarg>
@@ -63,6 +64,7 @@ struct Context {
     uint4* d_tw = nullptr;
     SharedBuf scratch;   // Y buffer of the two-pass NTT and of the asymmetric encode
     SharedBuf packed;    // repacked copy for unaligned device layouts
+    SharedBuf mixed;     // destination of the order-3 / order-9 step of the N = 3 * 2^k, 9 * 2^k transforms
     DevBuf staging;      // device copy for the host (T**) entry points (serialised by g_mu)
     std::map<uint32_t, TableSet> tables;              // per (mode, log2 N, ...)
     bool pin_caller = false;                          // fastecc_b200_pin_host_buffers()
@@ -86,11 +88,23 @@ int fail(int code, const char* fmt, ...)
 #define CUDA_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) \
     return fail(e_ == cudaErrorMemoryAllocation ? FASTECC_B200_ENOMEM : FASTECC_B200_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); } while (0)
 
-int check_shape(size_t N, size_t size, size_t max_log, const char* who)
+// N = r * 2^k with r = 3 or 9: the orders served by mixed_radix.cu on top of the power-of-two kernels (transforms only)
+uint32_t odd_factor(size_t N)
+{
+    if (!N) return 0;
+    while (!(N & 1)) N >>= 1;
+    return (uint32_t)(N <= 9 ? N : 0);
+}
+int check_shape(size_t N, size_t size, size_t max_log, const char* who, bool allow_mixed = false)
 {
     if (size == 0) return fail(FASTECC_B200_EINVAL, "%s: SIZE must be >= 1 word", who);
+    const uint32_t r = odd_factor(N);
+    if (allow_mixed && (r == 3 || r == 9) && is_pow2(N / r) && N / r <= ((size_t)1 << max_log)) {
+        if (size > 0xFFFFFFF0u) return fail(FASTECC_B200_EINVAL, "%s: SIZE too large", who);
+        return 0;
+    }
     if (!is_pow2(N) || N > ((size_t)1 << max_log))
-        return fail(FASTECC_B200_EINVAL, "%s: N=%zu must be a power of two in [1, 2^%zu] (P-1 = 2^20*4095)", who, N, max_log);
+        return fail(FASTECC_B200_EINVAL, "%s: N=%zu must be a power of two in [1, 2^%zu]%s (P-1 = 2^20*4095)", who, N, max_log, allow_mixed ? ", or 3 or 9 times one" : "");
     if (size > 0xFFFFFFF0u) return fail(FASTECC_B200_EINVAL, "%s: SIZE too large", who);
     return 0;
 }
@@ -164,6 +178,20 @@ int launch_plan(Context* c, std::vector<PassParams>& plan, cudaStream_t st, Pass
 int run_aligned(Context* c, uint32_t* x, size_t N, size_t size, size_t pitch, int mode /*0 fwd,1 inv,2 encode*/, cudaStream_t st, PassTimer* timer = nullptr)
 {
     const uint32_t pitch4 = (uint32_t)(pitch / 4), s4 = (uint32_t)((size + 3) / 4);
+    if (!is_pow2(N)) {                                    // N = r * M, r = 3 or 9 (mixed_radix.cu); transforms only
+        const uint32_t r = odd_factor(N);
+        const size_t M = N / r;
+        if (mode == 2 || (r != 3 && r != 9) || (unsigned long long)r * pitch > 0xFFFFFFF0ull) return fail(FASTECC_B200_EINVAL, "unsupported order N=%zu", N);
+        if (M > 1)                                        // step 1: r transforms of order M, each on every r-th row (row pitch r times larger), in place
+            for (uint32_t n1 = 0; n1 < r; ++n1)
+                if (int rc = run_aligned(c, x + (size_t)n1 * pitch, M, size, (size_t)r * pitch, mode, st)) return rc;
+        { std::lock_guard<std::mutex> lk(g_mu); CUDA_TRY(c->mixed.acquire(N * pitch * sizeof(uint32_t), st)); }
+        uint32_t* y = (uint32_t*)c->mixed.buf.p;          // step 2: twiddles + order-r transform, into natural order (out of place), then back
+        CUDA_TRY(launch_radix_pass(x, y, pitch4, s4, r, (uint32_t)M, mode == 1, c->d_tw, c->num_sms, st)); g_launches++;
+        CUDA_TRY(cudaMemcpy2DAsync(x, pitch * 4, y, pitch * 4, (size_t)s4 * 16 < pitch * 4 ? (size_t)s4 * 16 : pitch * 4, N, cudaMemcpyDeviceToDevice, st));
+        { std::lock_guard<std::mutex> lk(g_mu); CUDA_TRY(c->mixed.release_to(st)); }
+        return 0;
+    }
     if (N < ((size_t)1 << kMinLogR)) {
         const uint32_t z = (uint32_t)(gf::M / N) * (mode == 1 ? (uint32_t)-1 : 1u) & (gf::M - 1);
         const uint32_t q = mode == 2 ? (uint32_t)(gf::M / (2 * N)) : 0;
@@ -216,7 +244,7 @@ int run_dev(uint32_t* d, size_t N, size_t size, size_t pitch, int mode, void* st
     Context* c = g_ctx;
     if (!c) return fail(FASTECC_B200_ENOINIT, "%s: call fastecc_b200_init() first", who);
     if (!d) return fail(FASTECC_B200_EINVAL, "%s: null device pointer", who);
-    if (int rc = check_shape(N, size, mode == 2 ? FASTECC_B200_MAX_LOG_N_ENCODE : FASTECC_B200_MAX_LOG_N, who)) return rc;
+    if (int rc = check_shape(N, size, mode == 2 ? FASTECC_B200_MAX_LOG_N_ENCODE : FASTECC_B200_MAX_LOG_N, who, mode != 2)) return rc;
     if (pitch < size || pitch > 0xFFFFFFF0u) return fail(FASTECC_B200_EINVAL, "%s: pitch_words (%zu) must be in [SIZE_words (%zu), 2^32 - 16]", who, pitch, size);
     if ((unsigned long long)N * ((pitch + 3) / 4) >= (1ull << 32))
         return fail(FASTECC_B200_EINVAL, "%s: buffer of %zu x %zu words is 64 GiB or more (32-bit chunk indexing)", who, N, pitch);
@@ -239,7 +267,7 @@ int run_host(uint32_t** data, size_t N, size_t size, int mode, const char* who)
     Context* c = g_ctx;
     if (!c) return fail(FASTECC_B200_ENOINIT, "%s: call fastecc_b200_init() first", who);
     if (!data) return fail(FASTECC_B200_EINVAL, "%s: null block table", who);
-    if (int rc = check_shape(N, size, mode == 2 ? FASTECC_B200_MAX_LOG_N_ENCODE : FASTECC_B200_MAX_LOG_N, who)) return rc;
+    if (int rc = check_shape(N, size, mode == 2 ? FASTECC_B200_MAX_LOG_N_ENCODE : FASTECC_B200_MAX_LOG_N, who, mode != 2)) return rc;
     for (size_t i = 0; i < N; i++) if (!data[i]) return fail(FASTECC_B200_EINVAL, "%s: data[%zu] is null", who, i);
     std::lock_guard<std::mutex> host_lock(g_host_mu);
     const size_t pitch = (size + 3) / 4 * 4;
@@ -334,7 +362,7 @@ void fastecc_b200_shutdown(void)
     if (!g_ctx) return;
     cudaSetDevice(g_ctx->device);
     cudaDeviceSynchronize();
-    g_ctx->scratch.destroy(); g_ctx->packed.destroy(); g_ctx->staging.release();
+    g_ctx->scratch.destroy(); g_ctx->packed.destroy(); g_ctx->mixed.destroy(); g_ctx->staging.release();
     for (auto& r : g_ctx->registered) cudaHostUnregister(r.first);
     for (auto& kv : g_ctx->tables) for (auto& sl : kv.second.slots) { sl.buf.release(); if (sl.ready) cudaEventDestroy(sl.ready); }
     if (g_ctx->d_tw) cudaFree(g_ctx->d_tw);

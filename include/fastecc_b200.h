@@ -50,7 +50,10 @@ int  fastecc_b200_num_sms(void);
  * for <uint32_t,0xFFF00001>; call sites RS.cpp:41,63 and main.cpp:234,272,286.
  * data[i] -> SIZE words of block i (host memory, pageable or pinned).  In place: on return data[i] addresses
  * result block i; the pointer table itself is left untouched (the reference permutes it, callers only read
- * through data[i]).  The inverse transform is unnormalised, as in the reference.  1 <= N <= 2^20, power of two. */
+ * through data[i]).  The inverse transform is unnormalised, as in the reference.  1 <= N <= 2^20, power of two.
+ * Beyond MFA_NTT (which needs a power of two): N = 3 * 2^k and 9 * 2^k with 2^k <= 2^20 are accepted too -- the reference's
+ * order-3 / order-9 codelets (NTT3 ntt.cpp:26-46, NTT9 ntt.cpp:114-146) composed with the power-of-two transforms, result = the
+ * DFT with GF_Root(N) like Slow_NTT (ntt.cpp:451-483) -- so that block counts need not be rounded up (README.md:176). */
 int fastecc_b200_ntt_u32(uint32_t** data, size_t N, size_t SIZE_words, int inverse);
 
 /* Opt-in for callers that keep one large block array alive and transform it repeatedly from PAGEABLE memory, the way the
@@ -71,6 +74,7 @@ int fastecc_b200_rs_encode(uint32_t** data, size_t N, size_t SIZE_words);
  * are data.  The fast path needs d_blocks 16-byte aligned and pitch_words % 4 == 0 (columns are processed in
  * groups of 4 words, so up to 3 pad words per row are read and rewritten); other layouts go through an internal
  * repack.  stream: a cudaStream_t (NULL = default stream).  Asynchronous with respect to the host. */
+/* (N = 3 * 2^k, 9 * 2^k: transforms only; the encoder needs a power of two.) */
 int fastecc_b200_ntt_u32_dev  (uint32_t* d_blocks, size_t N, size_t SIZE_words, size_t pitch_words, int inverse, void* stream);
 int fastecc_b200_rs_encode_dev(uint32_t* d_blocks, size_t N, size_t SIZE_words, size_t pitch_words, void* stream);
 

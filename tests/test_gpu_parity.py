@@ -136,6 +136,32 @@ def test_elementwise_entry_points_match_oracle(fecc, oracle):
     assert np.array_equal(got[:, :S], want) and np.array_equal(got[:, S:], blk[:, S:])
 
 
+@pytest.mark.parametrize("N,S", [(3, 4), (9, 8), (6, 5), (18, 4), (12, 16), (36, 3), (96, 8), (288, 4), (3 * 64, 1024), (9 * 32, 40),
+                                 (3 * 1024, 8), (9 * 1024, 4), (3 * 2048, 4)])
+def test_orders_3_and_9_times_a_power_of_two(fecc, oracle, N, S):
+    """N = 3 * 2^k and 9 * 2^k (csrc/mixed_radix.cu on top of the power-of-two kernels) against the transform by definition
+    with GF_Root(N) (Slow_NTT, ntt.cpp:451-483, restated in the oracle), both directions, device and host entry points."""
+    a = ol.fill_B(oracle, N, S)
+    for inverse in (False, True):
+        want = a.copy()
+        oracle.oracle_slow_ntt(want.ctypes.data, N, S, 1 if inverse else 0)
+        assert np.array_equal(dev_ntt(fecc, a, inverse), want)
+        b = a.copy(); fecc.MFA_NTT(b, N, S, inverse); assert np.array_equal(b, want)
+
+
+@pytest.mark.parametrize("N", [3 << 16, 9 << 15, 3 << 18])
+def test_large_mixed_orders_round_trip(fecc, N):
+    """inverse(forward(x)) == N * x (mod P) on the device for orders too large for the O(N^2) oracle (S = 64 words)."""
+    import torch
+    g = torch.Generator(device="cuda"); g.manual_seed(N)
+    x = torch.randint(0, P, (N, 64), device="cuda", generator=g, dtype=torch.int64)
+    t = x.to(torch.int32)
+    fecc.ntt_dev(t, False)
+    assert int((t.long() & 0xFFFFFFFF).max()) < P
+    fecc.ntt_dev(t, True)
+    assert bool(((t.long() & 0xFFFFFFFF) == x * N % P).all())
+
+
 def test_host_scattered_blocks(fecc, oracle):
     """Blocks at arbitrary addresses, in permuted order (the reference leaves its own table permuted)."""
     N, S = 64, 12
@@ -332,9 +358,14 @@ def test_asymmetric_argument_validation(fecc):
 
 
 def test_argument_validation(fecc):
-    a = np.zeros((3, 4), dtype=np.uint32)
-    with pytest.raises(fecc.FastEccError) as e:
-        fecc.MFA_NTT(a, 3, 4, False)
+    for bad in (5, 7, 15, 27, 3 * 5, 9 * 3 * 4):                # neither 2^k nor 3 * 2^k nor 9 * 2^k
+        a = np.zeros((bad, 4), dtype=np.uint32)
+        with pytest.raises(fecc.FastEccError) as e:
+            fecc.MFA_NTT(a, bad, 4, False)
+        assert e.value.code == -1
+    a = np.zeros((6, 4), dtype=np.uint32)
+    with pytest.raises(fecc.FastEccError) as e:                 # the encoder is defined for powers of two only
+        fecc.EncodeReedSolomon_body(a, 6, 4)
     assert e.value.code == -1
     import torch
     t = torch.zeros((1 << 20, 4), dtype=torch.int32, device="cuda")
