@@ -162,6 +162,37 @@ def test_large_mixed_orders_round_trip(fecc, N):
     assert bool(((t.long() & 0xFFFFFFFF) == x * N % P).all())
 
 
+def test_dev_calls_on_two_streams_share_scratch_safely(fecc, oracle):
+    """Two-pass NTTs (which ping-pong through the context's ONE scratch buffer) and first-use table builds issued back to back
+    on two different streams: the library orders them with events (csrc/api.cu SharedBuf / TableSet), results must be exact."""
+    import torch
+    N, S = 1 << 13, 256
+    a = ol.fill_B(oracle, N, S)
+    b = (a[::-1] ^ np.uint32(0x5A5A5A5A)) % np.uint32(P)
+    want_a, want_b = ol.o_ntt(oracle, a, False), ol.o_ntt(oracle, np.ascontiguousarray(b), True)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(5):
+        ta, tb = to_dev(a), to_dev(np.ascontiguousarray(b))
+        torch.cuda.synchronize()
+        with torch.cuda.stream(s1):
+            fecc.ntt_dev(ta, False)
+        with torch.cuda.stream(s2):
+            fecc.ntt_dev(tb, True)
+        torch.cuda.synchronize()
+        assert np.array_equal(to_host(ta), want_a) and np.array_equal(to_host(tb), want_b)
+    N = 1 << 14                                                 # a fresh order: the tables built on s1 are used on s2 right away
+    c = ol.fill_B(oracle, N, 64)
+    want_c = ol.o_ntt(oracle, c, False)
+    t1, t2 = to_dev(c), to_dev(c)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s1):
+        fecc.ntt_dev(t1, False)
+    with torch.cuda.stream(s2):
+        fecc.ntt_dev(t2, False)
+    torch.cuda.synchronize()
+    assert np.array_equal(to_host(t1), want_c) and np.array_equal(to_host(t2), want_c)
+
+
 def test_host_scattered_blocks(fecc, oracle):
     """Blocks at arbitrary addresses, in permuted order (the reference leaves its own table permuted)."""
     N, S = 64, 12
@@ -285,8 +316,8 @@ def test_full_size_encode_linearity(fecc, oracle):
 
 @pytest.mark.parametrize("L,S", [(11, 16384), (12, 8192), (13, 4096), (14, 2048), (15, 1024), (16, 512), (17, 256), (18, 128), (19, 64), (20, 32)])
 def test_many_tiles_column_sample(fecc, oracle, L, S):
-    """128 MiB of blocks at every two-pass order: enough tiles per SM for the dual (two groups, three tile buffers)
-    schedule of the single-transform passes.  The transform is independent per word column, so a sample of columns of
+    """128 MiB of blocks at every two-pass order: many tiles per CTA, every set-table hand-over and strip shape of the
+    persistent tile loop.  The transform is independent per word column, so a sample of columns of
     the device result is compared with the oracle run on just those columns."""
     import torch
     N = 1 << L

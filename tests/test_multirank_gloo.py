@@ -1,6 +1,6 @@
-"""CPU, world_size 2, gloo: the N>1 host logic (stripe ownership, barrier/MAX timing rule, gather of parity hashes,
-aggregate metric).  Each rank encodes ITS OWN stripes with the CPU oracle standing in for the GPU call and rank 0
-checks every stripe's parity hash against a single-process run."""
+"""CPU, world_size 2, gloo: the N>1 host logic of the independent-stripes mode (stripe ownership, the MAX-over-ranks timing
+rule, gather of parity hashes, aggregate metric).  Each rank encodes ITS OWN stripes with the CPU oracle standing in for the GPU
+call and rank 0 checks every stripe's parity hash against a single-process run."""
 import os
 import socket
 import sys
@@ -17,6 +17,25 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
+def stripes_of(rank, world, n_stripes):
+    """Round-robin ownership: stripe s belongs to rank s % world."""
+    return list(range(rank, n_stripes, world))
+
+
+def gather_ints(values):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(list(values), dtype=torch.int64)
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [o.tolist() for o in out]
+
+
+def aggregate_throughput(bytes_per_stripe, stripes_per_rank, world, seconds):
+    """Whole-job GB/s: all ranks' bytes over the max-over-ranks time (weak scaling: per-GPU work is fixed)."""
+    return world * stripes_per_rank * bytes_per_stripe / seconds / 1e9
+
+
 def _worker(rank, world, port, n_stripes, L, S, q):
     import torch
     import torch.distributed as dist
@@ -25,7 +44,7 @@ def _worker(rank, world, port, n_stripes, L, S, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     o = ol.load_oracle()
-    mine = mr.stripes_of(rank, world, n_stripes)
+    mine = stripes_of(rank, world, n_stripes)
     hashes = []
     for s in mine:
         a = ol.fill_B(o, 1 << L, S)
@@ -33,18 +52,17 @@ def _worker(rank, world, port, n_stripes, L, S, q):
         hashes.append(ol.ohash(o, ol.o_encode(o, a)))
     dist.barrier()
     t = mr.max_over_ranks(0.25 * (rank + 1))         # pretend rank r took 0.25*(r+1) s
-    allh = mr.gather_ints(hashes)
+    allh = gather_ints(hashes)
     if rank == 0:
-        q.put((t, allh, mr.aggregate_throughput(1e9, len(mine), world, t)))
+        q.put((t, allh, aggregate_throughput(1e9, len(mine), world, t)))
     dist.destroy_process_group()
 
 
 def test_two_rank_stripe_sharding_gloo():
     import torch.multiprocessing as mp
     import oracle_lib as ol
-    from fastecc_b200 import multirank as mr
     world, n_stripes, L, S = 2, 4, 6, 5
-    assert mr.stripes_of(0, 2, 5) == [0, 2, 4] and mr.stripes_of(1, 2, 5) == [1, 3]
+    assert stripes_of(0, 2, 5) == [0, 2, 4] and stripes_of(1, 2, 5) == [1, 3]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
@@ -64,6 +82,6 @@ def test_two_rank_stripe_sharding_gloo():
         want.append(ol.ohash(o, ol.o_encode(o, a)))
     got = {}
     for r in range(world):
-        for s, h in zip(mr.stripes_of(r, world, n_stripes), allh[r]):
+        for s, h in zip(stripes_of(r, world, n_stripes), allh[r]):
             got[s] = h
     assert [got[s] for s in range(n_stripes)] == want
