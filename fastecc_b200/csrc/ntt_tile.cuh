@@ -121,6 +121,7 @@ FECC_HD Step step_of(uint32_t LR, uint32_t nxf, uint32_t s)
 {
     const uint32_t nr = num_rounds(LR);
     Step st;
+
     if (nxf == 1 || s + 1 < nr) { st.xfi = 0; st.k = s; st.fused = false; }
     else if (s + 1 == nr)       { st.xfi = 0; st.k = s; st.fused = true; }
     else                        { st.xfi = 1; st.k = s + 1 - nr; st.fused = false; }
@@ -378,7 +379,11 @@ FECC_HD void round_math(const PassParams& P, const Step st, uint32_t tid, uint32
     const Xform xf = get_xf(P, st.xfi);
     const bool plain = ((xf.t0 + set * xf.t1) & (gf::M - 1)) == 0;
     const uint4* tw = st.xfi ? tw1 : tw0;
-    if (st.k == 0 && plain) {
+    // The plain-round shortcut only in single-transform kernels (P.nxf is a compile-time constant there): in the fused kernel it would
+    // serve row set 0 and the small one-pass encodes, and its 1800 instructions between the two five-stage bodies cost the headline
+    // pass 3 % (instruction supply).  A plain transform through round_compute is the same arithmetic with
+    // table entries equal to 1.
+    if (st.k == 0 && plain && P.nxf == 1) {
         round0_plain(r.x, c, tw, first && P.prescale, P.pw, P.pwp_lo, P.pwp_hi);
     } else {
         if (first && P.prescale) prescale_all(r.x, P.pw, P.pwp_lo, P.pwp_hi);
