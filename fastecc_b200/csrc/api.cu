@@ -539,7 +539,7 @@ int fastecc_b200_rs_encode_shard_pass_p2p(const uint32_t* d_src, uint32_t* const
     cudaStream_t st = (cudaStream_t)stream;
     PassParams p = plan_encode_shard_p2p(d_src, d_peers, c->d_tw, (uint32_t)pitch, (uint32_t)size, N, (uint32_t)n_ranks, (uint32_t)rank, which);
     std::vector<PassParams> one{p};
-    if (int rc = attach_tables(c, 0x80000000u | (uint32_t)n_ranks << 16 | (uint32_t)rank << 8 | ilog2(N), one, st, which, 3)) return rc;
+    if (int rc = attach_tables(c, 0xA0000000u | (uint32_t)n_ranks << 16 | (uint32_t)rank << 8 | ilog2(N), one, st, which, 3)) return rc;
     CUDA_TRY(launch_pass(one[0], c->num_sms, st)); g_launches++;
     return 0;
 }
